@@ -1,0 +1,156 @@
+/*
+ * omg_b200 — C ABI of the B200-native OMG denoising hot path.
+ *
+ * The reference (kongzhecn/OMG) is pure Python on diffusers and has no FFI of its own; the
+ * "interface each entry point replaces" is therefore the torch / diffusers / xformers library call
+ * the reference makes at the cited line.  Ownership: the caller owns every buffer; the library only
+ * borrows raw device pointers for the duration of the call and keeps no state besides a per-process
+ * error string.  Every function returns 0 on success, non-zero on failure (omg_last_error() gives
+ * the message); nothing throws across the boundary.  All kernels are launched on the CUstream /
+ * cudaStream_t handle passed as `stream` (void*), never synchronise the host, and are CUDA-graph
+ * capturable.  fp16 storage, fp32 accumulation.  Activations are channels-last:
+ * (B, H, W, C) == (B, H*W tokens, C).
+ */
+#ifndef OMG_B200_H
+#define OMG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OMG_MAX_A 4
+#define OMG_MAX_SEGS 12
+
+/* Strided channels-last view: element (b,h,w,c) lives at ptr + b*sb + h*sh + w*sw + c (in elements). */
+typedef struct {
+    const void* ptr;
+    int32_t C, W, H, B;
+    int64_t sw, sh, sb;
+} omg_view4;
+
+/* One K-segment of a (implicit) GEMM: A operand = view a[a_idx] shifted by (dx,dy) pixels (out-of-range
+ * pixels read as zero = conv padding), channels [a_c0, a_c0+k_len); weight columns [b_k0, b_k0+k_len). */
+typedef struct {
+    int32_t a_idx, dx, dy, a_c0, k_len, b_k0;
+} omg_seg;
+
+enum { OMG_EPI_NONE = 0, OMG_EPI_GEGLU = 1, OMG_EPI_SILU = 2 };
+
+/*
+ * out[pix, n] = epi( sum_seg sum_k A_seg[pix+(dx,dy), k] * W[n, b_k0+k] + bias[n] + rowvec[b, n] ) + residual[pix, n]
+ *
+ * Replaces: torch.nn.Linear / Conv2d(3x3 | 1x1, stride 1 | 2) / peft LoRA delta / GEGLU inside
+ * diffusers UNet2DConditionModel.forward, reference call sites src/pipelines/lora_pipeline.py:546-566,592-599
+ * (cuBLAS / cuDNN in the reference).  tcgen05 tensor cores, TMA-staged operands.
+ * OMG_EPI_GEGLU: W rows (and bias) are interleaved (value_j, gate_j) pairs; out has N/2 channels,
+ * out_j = value_j * gelu_erf(gate_j).   OMG_EPI_SILU: epi(x) = x * sigmoid(x) (time-embedding MLPs).
+ */
+typedef struct {
+    omg_view4 a[OMG_MAX_A];
+    int32_t n_a;
+    omg_seg segs[OMG_MAX_SEGS];
+    int32_t n_segs;
+    const void* w;      /* [N, Ktot] row-major fp16 */
+    int32_t N, Ktot;
+    omg_view4 d;        /* output view; d.W/H/B define the pixel grid the tiles walk */
+    const void* bias;   /* [N] fp16 or NULL */
+    const void* rowvec; /* [B, rowvec_ld] fp16 or NULL: per-image additive vector (time-embedding projection) */
+    int32_t rowvec_ld;
+    const void* residual; /* contiguous [B*H*W, residual_ld] fp16 or NULL, added after the epilogue */
+    int32_t residual_ld;
+    int32_t epilogue;
+    int32_t block_n;    /* 0 = auto; else 64 | 128 | 160 | 256 */
+} omg_gemm_desc;
+
+int omg_gemm(const omg_gemm_desc* desc, void* stream);
+
+#define OMG_ATTN_MAX_ITEMS 16
+
+/*
+ * Flash attention, head_dim 64, fp32 softmax, probabilities never materialised:
+ *   out[out_b[i], :, h] = (accumulate ? out : 0) + out_weight * softmax(scale * Q[q_b[i],:,h] K[k_b[i],:,h]^T) V[v_b[i],:,h]
+ * for every item i and head h.  Q/K/V are row-major [batch, tokens, ld] fp16 with the head's 64 columns at
+ * col0 + 64*h.
+ *
+ * Replaces: attn.get_attention_scores + controller(probs) + torch.bmm in RegionControlNet_AttnProcessor
+ * (src/pipelines/lora_pipeline.py:114-116) with the prompt-to-prompt edit of src/prompt_attention/p2p_attention.py:
+ * 124-138 folded into the (q_b, k_b, v_b) remap; xformers.ops.memory_efficient_attention / F.scaled_dot_product_
+ * attention of the concept UNet (src/ip_adapter/attention_processor.py:197-204,383-401); and the decoupled
+ * text + scale*ip sum (attention_processor.py:370-409) via accumulate/out_weight.
+ */
+typedef struct {
+    const void* q; int32_t q_ld; int64_t q_bs; int32_t q_col0;
+    const void* k; int32_t k_ld; int64_t k_bs; int32_t k_col0;
+    const void* v; int32_t v_ld; int64_t v_bs; int32_t v_col0;
+    void* out;     int32_t out_ld; int64_t out_bs; int32_t out_col0;
+    int32_t n_q, n_kv, heads, head_dim;
+    int32_t n_items;
+    int32_t out_b[OMG_ATTN_MAX_ITEMS], q_b[OMG_ATTN_MAX_ITEMS], k_b[OMG_ATTN_MAX_ITEMS], v_b[OMG_ATTN_MAX_ITEMS];
+    float scale;      /* softmax scale, head_dim^-0.5 */
+    float out_weight; /* weight of this term */
+    int32_t accumulate;
+} omg_attn_desc;
+
+int omg_attention(const omg_attn_desc* desc, void* stream);
+
+/*
+ * GroupNorm(32 groups) over channels-last fp16, optional SiLU, input = channel-concatenation of (x1 | x2).
+ * y[B, HW, C1+C2].  stats_ws: B*64 floats of scratch.  Replaces torch GroupNorm + SiLU + torch.cat inside diffusers
+ * ResnetBlock2D / Transformer2DModel / UNet up-blocks [3P] (call site src/pipelines/lora_pipeline.py:546-566).
+ */
+int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, const void* gamma, const void* beta,
+                  float eps, int silu, void* stats_ws, void* y, void* stream);
+
+/* LayerNorm over the last dim of [rows, C] fp16 (BasicTransformerBlock norm1/2/3 [3P]). */
+int omg_layernorm(const void* x, const void* gamma, const void* beta, void* y, long long rows, int C, float eps,
+                  void* stream);
+
+#define OMG_MAX_CONCEPTS 8
+
+/*
+ * One denoising-step tail in a single launch: region noise fusion, classifier-free guidance, Euler-discrete step,
+ * and the next step's scaled model inputs.  Replaces src/pipelines/lora_pipeline.py:568-615 and :491-492,583-585
+ * (src/pipelines/instantid_pipeline.py:618-690).
+ *   noise_main [4, HW, 8] fp16 rows (uncond0, uncond1, cond0, cond1), channels 0..3 used;
+ *   noise_concept[k] [2, HW, 8] rows (uncond, cond); mask[k] [HW] float {0,1} or NULL (concept skipped);
+ *   image-1 rows: eps = (1 - U) * eps_main + sum_k M_k * eps_k with U = OR_k M_k;
+ *   eps = eps_u + guidance * (eps_c - eps_u);  latents += eps * (sigma_next - sigma)   (fp32 state [2, HW, 4]);
+ *   next_main_in [4, HW, 8] = latents / sqrt(sigma_next^2 + 1) in row order (img0, img1, img0, img1);
+ *   next_concept_in [2, HW, 8] = scaled image-1 latent twice; latents_f16 optional fp16 copy [2, HW, 4].
+ */
+typedef struct {
+    const void* noise_main;
+    const void* noise_concept[OMG_MAX_CONCEPTS];
+    const void* mask[OMG_MAX_CONCEPTS];
+    int32_t n_concepts;
+    float guidance, sigma, sigma_next;
+    void* latents;
+    void* next_main_in;
+    void* next_concept_in;
+    void* latents_f16;
+    int32_t HW;
+} omg_fuse_desc;
+
+int omg_fuse_step(const omg_fuse_desc* desc, void* stream);
+
+/*
+ * out[b, w, :] = sum_n coef[w, n] * ctx[b, n, :]  (fp16 ctx/out [B, L, C], fp32 coef [L, L]).  Builds the
+ * prompt-to-prompt edited context  M diag(alpha) ctx  /  diag(1-alpha) ctx  so that the cross-attention edit
+ * P0 M * alpha + (1-alpha) P1  (src/prompt_attention/p2p_attention.py:131-134,146-147) becomes two plain attention
+ * terms over projected V.
+ */
+int omg_ctx_mix(const void* ctx, const void* coef, void* out, int B, int L, int C, void* stream);
+
+/* Error string of the last failing call on this thread (never NULL). */
+const char* omg_last_error(void);
+/* Library / build identification: returns e.g. "omg_b200 sm_100a". */
+const char* omg_version(void);
+/* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */
+uint64_t omg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,365 @@
+// Flash attention on tcgen05 for the SDXL transformer blocks (head_dim 64): self-attention (N = 1024 / 4096 keys)
+// and cross-attention (77 text keys, 16 IP-adapter keys), never materialising the probability matrix.
+//
+// Prompt-to-prompt control and decoupled (IP-adapter) attention are expressed through the descriptor instead of
+// through a probability callback (reference: src/pipelines/lora_pipeline.py:114-116 + src/prompt_attention/
+// p2p_attention.py:124-138, src/ip_adapter/attention_processor.py:370-409):
+//   * every output batch row names the batch rows its Q, K and V come from  -> "replace self-attention"
+//     out_1 = softmax(Q_0 K_0^T) V_1 is a pointer remap;
+//   * `accumulate` + `out_weight` add a second separately-normalised term    -> txt + scale * ip, and the general
+//     cross-attention edit  P_0 (M diag(a) V_1) + P_1 (diag(1-a) V_1).
+//
+// CTA = one (item, head, 256-query slab): two 128-row Q tiles ping-pong through one MMA issuer so the tensor core
+// works on one tile while the other tile's softmax runs.  320 threads: warp 0 TMA, warp 1 tcgen05.mma issuer,
+// warps 2-5 / 6-9 softmax groups (one query row per thread; TMEM lane == row, so no shuffles are needed).
+// TMEM: S0 | S1 (128 cols each, fp32 scores) | O[group][2] (64 cols each, per-KV-block P.V partials).
+#include <cuda_fp16.h>
+#include <math.h>
+#include <string.h>
+
+#include "../../include/omg_b200.h"
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace omg {
+
+constexpr int ATT_THREADS = 320;
+constexpr int ATT_BQ = 128;   // rows per softmax group
+constexpr int ATT_BKV = 128;  // keys per block
+constexpr int ATT_D = 64;
+constexpr int ATT_KV_STAGES = 3;
+constexpr int ATT_Q_BYTES = ATT_BQ * ATT_D * 2;       // 16 KB
+constexpr int ATT_KV_BYTES = ATT_BKV * ATT_D * 2;     // 16 KB (K) ; V same
+constexpr int ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;     // 32 KB
+constexpr int ATT_SMEM = 1024 + 2 * ATT_Q_BYTES + ATT_KV_STAGES * 2 * ATT_KV_BYTES + 2 * ATT_P_BYTES + 512;
+
+struct alignas(64) AttnParams {
+    CUtensorMap q_map, k_map, v_map;  // 3D (cols, tokens, batch), box (64, 128, 1), SWIZZLE_128B
+    __half* out;
+    int out_ld;
+    long long out_bs;
+    int n_q, n_kv, heads;
+    int q_col0, k_col0, v_col0, out_col0;
+    int n_items;
+    int out_b[OMG_ATTN_MAX_ITEMS], q_b[OMG_ATTN_MAX_ITEMS], k_b[OMG_ATTN_MAX_ITEMS], v_b[OMG_ATTN_MAX_ITEMS];
+    float scale_log2;  // softmax scale * log2(e)
+    float out_weight;
+    int accumulate;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* q_smem = smem;                                  // 2 x 16 KB
+    uint8_t* kv_smem = q_smem + 2 * ATT_Q_BYTES;             // stages x (K 16 KB | V 16 KB)
+    uint8_t* p_smem = kv_smem + ATT_KV_STAGES * 2 * ATT_KV_BYTES;  // 2 x 32 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + 2 * ATT_P_BYTES);
+    uint64_t* q_full = bars;                      // 1
+    uint64_t* kv_full = bars + 1;                 // 3
+    uint64_t* kv_empty = kv_full + ATT_KV_STAGES; // 3
+    uint64_t* s_full = kv_empty + ATT_KV_STAGES;  // 2
+    uint64_t* p_full = s_full + 2;                // 2
+    uint64_t* p_empty = p_full + 2;               // 2
+    uint64_t* o_full = p_empty + 2;               // 2 x 2  [g*2 + buf]
+    uint64_t* o_empty = o_full + 4;               // 2 x 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int slab = blockIdx.x;  // 256-query slab
+    const int head = blockIdx.y;
+    const int item = blockIdx.z;
+    const int nkv = (p.n_kv + ATT_BKV - 1) / ATT_BKV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.q_map);
+        tma_prefetch_desc(&p.k_map);
+        tma_prefetch_desc(&p.v_map);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < ATT_KV_STAGES; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&s_full[g], 1);
+            mbar_init(&p_full[g], 4);
+            mbar_init(&p_empty[g], 1);
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(&o_full[g * 2 + b], 1);
+                mbar_init(&o_empty[g * 2 + b], 4);
+            }
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: S_g at g*128, O_g[buf] at 256 + g*128 + buf*64
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, 2 * ATT_Q_BYTES);
+            const int qb = p.q_b[item];
+            tma_load_3d(q_smem, &p.q_map, q_full, p.q_col0 + head * ATT_D, slab * 256, qb);
+            tma_load_3d(q_smem + ATT_Q_BYTES, &p.q_map, q_full, p.q_col0 + head * ATT_D, slab * 256 + 128, qb);
+            int stage = 0;
+            uint32_t phase = 0;
+            const int kb = p.k_b[item], vb = p.v_b[item];
+            for (int j = 0; j < nkv; ++j) {
+                mbar_wait(&kv_empty[stage], phase ^ 1);
+                uint8_t* kd = kv_smem + stage * 2 * ATT_KV_BYTES;
+                mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_KV_BYTES);
+                tma_load_3d(kd, &p.k_map, &kv_full[stage], p.k_col0 + head * ATT_D, j * ATT_BKV, kb);
+                tma_load_3d(kd + ATT_KV_BYTES, &p.v_map, &kv_full[stage], p.v_col0 + head * ATT_D, j * ATT_BKV, vb);
+                if (++stage == ATT_KV_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = umma_idesc_f16(128, ATT_BKV, false, false);  // S = Q K^T
+            constexpr uint32_t idesc_o = umma_idesc_f16(128, ATT_D, false, true);     // O = P V (V is N-major)
+            auto issue_s = [&](int g, int stage) {
+                const uint64_t a = umma_desc_sw128(smem_u32(q_smem + g * ATT_Q_BYTES), 1024, 16);
+                const uint64_t b = umma_desc_sw128(smem_u32(kv_smem + stage * 2 * ATT_KV_BYTES), 1024, 16);
+#pragma unroll
+                for (int k = 0; k < ATT_D / 16; ++k)
+                    tc_mma_f16_ss(tmem_base + g * 128, a + 2 * k, b + 2 * k, idesc_s, k > 0);
+                tc_commit(&s_full[g]);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_s(0, 0);
+            issue_s(1, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int j = 0; j < nkv; ++j) {
+                int nstage = stage + 1;
+                uint32_t nphase = phase;
+                if (nstage == ATT_KV_STAGES) {
+                    nstage = 0;
+                    nphase ^= 1;
+                }
+                const int ob = j & 1;
+                for (int g = 0; g < 2; ++g) {
+                    mbar_wait(&p_full[g], j & 1);
+                    mbar_wait(&o_empty[g * 2 + ob], ((j >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t p_addr = smem_u32(p_smem + g * ATT_P_BYTES);
+                    const uint32_t v_addr = smem_u32(kv_smem + stage * 2 * ATT_KV_BYTES + ATT_KV_BYTES);
+                    const uint32_t d_tmem = tmem_base + 256 + g * 128 + ob * 64;
+#pragma unroll
+                    for (int k = 0; k < ATT_BKV / 16; ++k) {
+                        // A = P: K-major, two 64-wide (16 KB) halves; B = V: 16 key rows (2 KB) per K step
+                        const uint64_t a = umma_desc_sw128(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 1024, 16);
+                        const uint64_t b = umma_desc_sw128(v_addr + k * 2048, 1024, 1024);
+                        tc_mma_f16_ss(d_tmem, a, b, idesc_o, k > 0);
+                    }
+                    tc_commit(&o_full[g * 2 + ob]);
+                    tc_commit(&p_empty[g]);
+                    if (j + 1 < nkv) {
+                        mbar_wait(&kv_full[nstage], nphase);
+                        tc_fence_after();
+                        issue_s(g, nstage);
+                    }
+                }
+                tc_commit(&kv_empty[stage]);
+                stage = nstage;
+                phase = nphase;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax groups
+        const int g = (warp - 2) >> 2;
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t s_tmem = tmem_base + g * 128 + lane_base;
+        uint8_t* my_p = p_smem + g * ATT_P_BYTES;
+        float m = -INFINITY, l = 0.f, corr_prev = 0.f;
+        float o_acc[ATT_D];
+#pragma unroll
+        for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.f;
+
+        auto accumulate_o = [&](int jb, float corr) {
+            const int ob = jb & 1;
+            mbar_wait(&o_full[g * 2 + ob], (jb >> 1) & 1);
+            tc_fence_after();
+            const uint32_t o_tmem = tmem_base + 256 + g * 128 + ob * 64 + lane_base;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(o_tmem + c * 32, r);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * corr + __uint_as_float(r[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_empty[g * 2 + ob]);
+        };
+
+        for (int j = 0; j < nkv; ++j) {
+            mbar_wait(&s_full[g], j & 1);
+            tc_fence_after();
+            const int kv_left = p.n_kv - j * ATT_BKV;  // valid keys in this block (>= 1)
+            // pass 1: row maximum
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(s_tmem + c * 32, r);
+                tc_wait_ld();
+                if (kv_left >= (c + 1) * 32) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i < kv_left) mx = fmaxf(mx, __uint_as_float(r[i]));
+                }
+            }
+            const float m_new = fmaxf(m, mx * p.scale_log2);
+            const float corr = fast_exp2(m - m_new);  // m == -inf on the first block -> 0
+            m = m_new;
+            // P buffer must have been consumed by the previous block's P.V
+            mbar_wait(&p_empty[g], (j & 1) ^ 1);
+            float sum = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(s_tmem + c * 32, r);
+                tc_wait_ld();
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float p0 = fast_exp2(__uint_as_float(r[2 * i]) * p.scale_log2 - m_new);
+                    float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * p.scale_log2 - m_new);
+                    if (c * 32 + 2 * i >= kv_left) p0 = 0.f;
+                    if (c * 32 + 2 * i + 1 >= kv_left) p1 = 0.f;
+                    // the row sum uses the fp16-rounded probabilities the tensor core will consume
+                    const __half2 h = __floats2half2_rn(p0, p1);
+                    const float2 f = __half22float2(h);
+                    sum += f.x + f.y;
+                    pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                // K-major SWIZZLE_128B: half hh = c >> 1, 16 B chunk index within the 128 B row = (c & 1) * 4 + t
+                uint8_t* rowp = my_p + (c >> 1) * 16384 + row * 128;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int chunk = ((c & 1) * 4 + t) ^ (row & 7);
+                    *reinterpret_cast<uint4*>(rowp + chunk * 16) =
+                        make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+                }
+            }
+            l = l * corr + sum;
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[g]);
+            if (j > 0) accumulate_o(j - 1, corr_prev);
+            corr_prev = corr;
+        }
+        accumulate_o(nkv - 1, corr_prev);
+
+        // finalise: out = (accumulate ? out : 0) + w * O / l
+        const int qrow = slab * 256 + g * 128 + row;
+        if (qrow < p.n_q) {
+            const float inv = p.out_weight / l;
+            __half* op = p.out + (long long)p.out_b[item] * p.out_bs + (long long)qrow * p.out_ld + p.out_col0 +
+                         head * ATT_D;
+            uint4* op4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = o_acc[t * 8 + i] * inv;
+                if (p.accumulate) {
+                    const uint4 u = op4[t];
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 f = __half22float2(h2[i]);
+                        v[2 * i] += f.x;
+                        v[2 * i + 1] += f.y;
+                    }
+                }
+                op4[t] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
+                                    pack_half2(v[6], v[7]));
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static int make_attn_map(CUtensorMap* m, const void* ptr, int cols, int ld, int tokens, long long bs, int nb) {
+    const uint64_t dims[3] = {(uint64_t)cols, (uint64_t)tokens, (uint64_t)nb};
+    const uint64_t strides[3] = {1, (uint64_t)ld, (uint64_t)bs};
+    const uint32_t box[3] = {64, 128, 1};
+    return make_tmap_f16(m, ptr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace omg
+
+using namespace omg;
+
+extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    OMG_CHECK(d != nullptr, "omg_attention: null descriptor");
+    OMG_CHECK(d->head_dim == 64, "omg_attention: head_dim %d unsupported (SDXL uses 64)", d->head_dim);
+    OMG_CHECK(d->n_items >= 1 && d->n_items <= OMG_ATTN_MAX_ITEMS, "omg_attention: n_items=%d out of range",
+              d->n_items);
+    OMG_CHECK(d->n_q >= 1 && d->n_kv >= 1 && d->heads >= 1, "omg_attention: empty problem");
+    OMG_CHECK(d->q && d->k && d->v && d->out, "omg_attention: null pointer");
+    OMG_CHECK(d->out_ld % 8 == 0 && d->out_col0 % 8 == 0 && d->out_bs % 8 == 0,
+              "omg_attention: output must be 16 B aligned per row");
+    static bool configured = false;
+    if (!configured) {
+        OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        configured = true;
+    }
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    int max_qb = 0, max_kb = 0, max_vb = 0;
+    for (int i = 0; i < d->n_items; ++i) {
+        p.out_b[i] = d->out_b[i];
+        p.q_b[i] = d->q_b[i];
+        p.k_b[i] = d->k_b[i];
+        p.v_b[i] = d->v_b[i];
+        max_qb = d->q_b[i] > max_qb ? d->q_b[i] : max_qb;
+        max_kb = d->k_b[i] > max_kb ? d->k_b[i] : max_kb;
+        max_vb = d->v_b[i] > max_vb ? d->v_b[i] : max_vb;
+        OMG_CHECK(d->out_b[i] >= 0 && d->q_b[i] >= 0 && d->k_b[i] >= 0 && d->v_b[i] >= 0,
+                  "omg_attention: negative batch index in item %d", i);
+    }
+    const int cols = d->heads * 64;
+    if (make_attn_map(&p.q_map, d->q, d->q_col0 + cols, d->q_ld, d->n_q, d->q_bs, max_qb + 1)) return 1;
+    if (make_attn_map(&p.k_map, d->k, d->k_col0 + cols, d->k_ld, d->n_kv, d->k_bs, max_kb + 1)) return 1;
+    if (make_attn_map(&p.v_map, d->v, d->v_col0 + cols, d->v_ld, d->n_kv, d->v_bs, max_vb + 1)) return 1;
+    p.out = static_cast<__half*>(d->out);
+    p.out_ld = d->out_ld;
+    p.out_bs = d->out_bs;
+    p.n_q = d->n_q;
+    p.n_kv = d->n_kv;
+    p.heads = d->heads;
+    p.q_col0 = d->q_col0;
+    p.k_col0 = d->k_col0;
+    p.v_col0 = d->v_col0;
+    p.out_col0 = d->out_col0;
+    p.n_items = d->n_items;
+    p.scale_log2 = d->scale * 1.4426950408889634f;
+    p.out_weight = d->out_weight;
+    p.accumulate = d->accumulate;
+    dim3 grid((d->n_q + 255) / 256, d->heads, d->n_items);
+    attn_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(p);
+    return check_launch("attn_tc_kernel");
+}

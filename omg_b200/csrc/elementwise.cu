@@ -1,0 +1,166 @@
+// HBM-bound element-wise kernels of the denoising step.
+//
+// omg_fuse_step: region noise fusion + classifier-free guidance + Euler step + next-step model inputs in ONE
+// launch (reference: src/pipelines/lora_pipeline.py:568-615 does this with ~15 boolean-index kernels, each
+// forcing a host sync through nonzero(); src/pipelines/instantid_pipeline.py:618-690 is identical).
+// Algorithmic bytes per launch (HW latent pixels, n concepts): read (4 + 2n) * HW*8*2 B noise + n * HW*4 B masks
+// + HW*2*4*4 B latents; write HW*2*4*4 B latents + 6 * HW*8*2 B next inputs.
+#include <cuda_fp16.h>
+
+#include "../../include/omg_b200.h"
+#include "host_common.h"
+
+namespace omg {
+
+struct FuseParams {
+    const __half* noise_main;                          // [4, HW, 8]  rows: uncond0, uncond1, cond0, cond1
+    const __half* noise_concept[OMG_MAX_CONCEPTS];     // [2, HW, 8]  rows: uncond, cond
+    const float* mask[OMG_MAX_CONCEPTS];               // [HW] in {0,1}
+    int n_concepts;
+    float guidance, sigma, sigma_next;
+    float* latents;          // [2, HW, 4] fp32 state (image 0 = layout, image 1 = edited)
+    __half* next_main_in;    // [4, HW, 8] = scale_model_input(cat([latents]*2)), channels 4..7 zero
+    __half* next_concept_in; // [2, HW, 8] = scaled latent of image 1, twice
+    __half* latents_f16;     // optional [2, HW, 4] fp16 copy of the new latents (pipeline output)
+    int HW;
+};
+
+__device__ __forceinline__ void load4(const __half* p, float (&v)[4]) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+    const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+__global__ void fuse_step_kernel(FuseParams p) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= p.HW) return;
+    const size_t HW = p.HW;
+    float u0[4], u1[4], c0[4], c1[4];
+    load4(p.noise_main + (0 * HW + pix) * 8, u0);
+    load4(p.noise_main + (1 * HW + pix) * 8, u1);
+    load4(p.noise_main + (2 * HW + pix) * 8, c0);
+    load4(p.noise_main + (3 * HW + pix) * 8, c1);
+    if (p.n_concepts > 0) {
+        // union mask zeroes the main prediction of image 1, every concept adds its own prediction inside its mask
+        bool any = false;
+        float au[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0};
+        for (int k = 0; k < p.n_concepts; ++k) {
+            if (p.mask[k] == nullptr) continue;
+            if (p.mask[k][pix] == 1.0f) {
+                any = true;
+                float ku[4], kc[4];
+                load4(p.noise_concept[k] + (0 * HW + pix) * 8, ku);
+                load4(p.noise_concept[k] + (1 * HW + pix) * 8, kc);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    au[i] += ku[i];
+                    ac[i] += kc[i];
+                }
+            }
+        }
+        if (any) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                u1[i] = au[i];
+                c1[i] = ac[i];
+            }
+        }
+    }
+    const float dt = p.sigma_next - p.sigma;
+    const float in_scale = rsqrtf(p.sigma_next * p.sigma_next + 1.0f);
+    float4 l0 = *reinterpret_cast<float4*>(p.latents + (0 * HW + pix) * 4);
+    float4 l1 = *reinterpret_cast<float4*>(p.latents + (1 * HW + pix) * 4);
+    float e0[4], e1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        e0[i] = u0[i] + p.guidance * (c0[i] - u0[i]);
+        e1[i] = u1[i] + p.guidance * (c1[i] - u1[i]);
+    }
+    l0.x += e0[0] * dt; l0.y += e0[1] * dt; l0.z += e0[2] * dt; l0.w += e0[3] * dt;
+    l1.x += e1[0] * dt; l1.y += e1[1] * dt; l1.z += e1[2] * dt; l1.w += e1[3] * dt;
+    *reinterpret_cast<float4*>(p.latents + (0 * HW + pix) * 4) = l0;
+    *reinterpret_cast<float4*>(p.latents + (1 * HW + pix) * 4) = l1;
+    if (p.latents_f16) {
+        __half2* o0 = reinterpret_cast<__half2*>(p.latents_f16 + (0 * HW + pix) * 4);
+        __half2* o1 = reinterpret_cast<__half2*>(p.latents_f16 + (1 * HW + pix) * 4);
+        o0[0] = __floats2half2_rn(l0.x, l0.y); o0[1] = __floats2half2_rn(l0.z, l0.w);
+        o1[0] = __floats2half2_rn(l1.x, l1.y); o1[1] = __floats2half2_rn(l1.z, l1.w);
+    }
+    uint4 s0, s1;
+    {
+        __half2* h = reinterpret_cast<__half2*>(&s0);
+        h[0] = __floats2half2_rn(l0.x * in_scale, l0.y * in_scale);
+        h[1] = __floats2half2_rn(l0.z * in_scale, l0.w * in_scale);
+        h[2] = h[3] = __floats2half2_rn(0.f, 0.f);
+        h = reinterpret_cast<__half2*>(&s1);
+        h[0] = __floats2half2_rn(l1.x * in_scale, l1.y * in_scale);
+        h[1] = __floats2half2_rn(l1.z * in_scale, l1.w * in_scale);
+        h[2] = h[3] = __floats2half2_rn(0.f, 0.f);
+    }
+    if (p.next_main_in) {
+        uint4* o = reinterpret_cast<uint4*>(p.next_main_in);
+        o[0 * HW + pix] = s0;
+        o[1 * HW + pix] = s1;
+        o[2 * HW + pix] = s0;
+        o[3 * HW + pix] = s1;
+    }
+    if (p.next_concept_in) {
+        uint4* o = reinterpret_cast<uint4*>(p.next_concept_in);
+        o[0 * HW + pix] = s1;
+        o[1 * HW + pix] = s1;
+    }
+}
+
+// out[b, w, :] = sum_n coef[w, n] * ctx[b, n, :]   (coef = M diag(alpha) or diag(1 - alpha); L = 77)
+__global__ void ctx_mix_kernel(const __half* __restrict__ ctx, const float* __restrict__ coef, __half* __restrict__ out,
+                               int L, int C) {
+    const int b = blockIdx.z, w = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float acc = 0.f;
+    for (int n = 0; n < L; ++n) {
+        const float a = coef[w * L + n];
+        if (a != 0.f) acc += a * __half2float(ctx[((size_t)b * L + n) * C + c]);
+    }
+    out[((size_t)b * L + w) * C + c] = __float2half_rn(acc);
+}
+
+}  // namespace omg
+
+using namespace omg;
+
+extern "C" int omg_fuse_step(const omg_fuse_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    OMG_CHECK(d && d->noise_main && d->latents, "omg_fuse_step: null pointer");
+    OMG_CHECK(d->n_concepts >= 0 && d->n_concepts <= OMG_MAX_CONCEPTS, "omg_fuse_step: n_concepts=%d out of range",
+              d->n_concepts);
+    OMG_CHECK(d->HW >= 1, "omg_fuse_step: empty latent");
+    FuseParams p;
+    p.noise_main = static_cast<const __half*>(d->noise_main);
+    for (int k = 0; k < OMG_MAX_CONCEPTS; ++k) {
+        p.noise_concept[k] = k < d->n_concepts ? static_cast<const __half*>(d->noise_concept[k]) : nullptr;
+        p.mask[k] = k < d->n_concepts ? static_cast<const float*>(d->mask[k]) : nullptr;
+        OMG_CHECK(k >= d->n_concepts || p.mask[k] == nullptr || p.noise_concept[k] != nullptr,
+                  "omg_fuse_step: concept %d has a mask but no noise prediction", k);
+    }
+    p.n_concepts = d->n_concepts;
+    p.guidance = d->guidance;
+    p.sigma = d->sigma;
+    p.sigma_next = d->sigma_next;
+    p.latents = static_cast<float*>(d->latents);
+    p.next_main_in = static_cast<__half*>(d->next_main_in);
+    p.next_concept_in = static_cast<__half*>(d->next_concept_in);
+    p.latents_f16 = static_cast<__half*>(d->latents_f16);
+    p.HW = d->HW;
+    fuse_step_kernel<<<(d->HW + 127) / 128, 128, 0, stream>>>(p);
+    return check_launch("fuse_step_kernel");
+}
+
+extern "C" int omg_ctx_mix(const void* ctx, const void* coef, void* out, int B, int L, int C, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    OMG_CHECK(ctx && coef && out && B >= 1 && L >= 1 && C >= 1, "omg_ctx_mix: bad arguments");
+    ctx_mix_kernel<<<dim3((C + 127) / 128, L, B), 128, 0, stream>>>(
+        static_cast<const __half*>(ctx), static_cast<const float*>(coef), static_cast<__half*>(out), L, C);
+    return check_launch("ctx_mix_kernel");
+}

@@ -1,0 +1,453 @@
+// Persistent tcgen05 implicit-GEMM for every Linear / Conv2d / LoRA / GEGLU of the SDXL UNet.
+//
+//   out[pix, n] = epi( sum_seg sum_k A_seg[pix + (dx,dy), k] * W[n, b_k0 + k] + bias[n] + rowvec[b, n] ) + residual
+//
+// * Activations are channels-last, so a 3x3 conv is 9 K-segments whose A tiles are the SAME tensor read
+//   through TMA at shifted pixel coordinates (hardware zero-fill = padding); no im2col buffer exists.
+//   Stride-2 convs and nearest-2x-upsample convs use strided "phase" views of the tensor as A / D maps.
+//   A ResBlock's 1x1 shortcut and a LoRA delta  s*B(Ax)  are just more K-segments of the same accumulator.
+// * One CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (single thread) + TMEM
+//   owner, warps 2..5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store).  Two TMEM accumulator
+//   stages so the epilogue of tile i overlaps the mainloop of tile i+1.
+// * Tile 128 (pixels) x BN (channels) x 64 (K); operands land in smem in the 128B-swizzled K-major layout
+//   the UMMA descriptors expect.
+//
+// Roofline: tensor-bound (ridge ~227 flop/B); algorithmic FLOPs per launch = 2 * pixels * N * sum(k_len).
+#include <cuda_fp16.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "../../include/omg_b200.h"
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace omg {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;
+constexpr int STAGING_BYTES = 4 * 2 * 2048;  // 4 epilogue warps x double buffer x (32 rows x 64 B)
+
+struct SegDev {
+    int a_map, dx, dy, a_c0, k_blocks, b_k0;
+};
+
+struct alignas(64) GemmParams {
+    CUtensorMap a_maps[OMG_MAX_A];
+    CUtensorMap b_map;
+    CUtensorMap d_map;
+    SegDev segs[OMG_MAX_SEGS];
+    int n_segs;
+    int m_tiles, n_tiles;
+    int tw, th, tiles_w, tiles_h;
+    int store_w, store_h;
+    int img_w, img_h;
+    int N, N_out;
+    const __half* bias;
+    const __half* rowvec;
+    int rowvec_ld;
+    const __half* residual;
+    int residual_ld;
+    int act_silu;
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - STAGING_BYTES - 256 * 4 /*bias*/ - 256 /*bars*/;
+    static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + 256 * 4 + 256;
+    static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator stage
+    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+    float* s_bias = reinterpret_cast<float*>(staging + STAGING_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + 256);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < OMG_MAX_A; ++i) tma_prefetch_desc(&p.a_maps[i]);
+        tma_prefetch_desc(&p.b_map);
+        tma_prefetch_desc(&p.d_map);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------- TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
+                const int b = m_tile / tiles_per_img;
+                const int rem = m_tile % tiles_per_img;
+                const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
+                const int n0 = n_tile * BN;
+                for (int s = 0; s < p.n_segs; ++s) {
+                    const SegDev sg = p.segs[s];
+                    for (int kb = 0; kb < sg.k_blocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+                        uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        tma_load_4d(a_dst, &p.a_maps[sg.a_map], &full_bar[stage], sg.a_c0 + kb * BK, w0 + sg.dx,
+                                    h0 + sg.dy, b);
+                        tma_load_2d(b_dst, &p.b_map, &full_bar[stage], sg.b_k0 + kb * BK, n0);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------- MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(BM, BN, false, false);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+                uint32_t accumulate = 0;
+                for (int s = 0; s < p.n_segs; ++s) {
+                    const int kbs = p.segs[s].k_blocks;
+                    for (int kb = 0; kb < kbs; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                        const uint64_t a_desc = umma_desc_sw128(a_addr, 1024, 16);
+                        const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::A_BYTES, 1024, 16);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // +32 B per K=16 step inside the 128 B swizzle atom (start-address field is >>4)
+                            tc_mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate);
+                            accumulate = 1;
+                        }
+                        tc_commit(&empty_bar[stage]);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+                tc_commit(&tfull_bar[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------- epilogue warps
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int et = q * 32 + lane;  // row of the tile owned by this thread
+        uint8_t* my_stage = staging + q * 4096;
+        int buf = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        constexpr int ACC_PER_CHUNK = (EPI == OMG_EPI_GEGLU) ? 64 : 32;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
+            const int b = m_tile / tiles_per_img;
+            const int rem = m_tile % tiles_per_img;
+            const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
+            const int n0 = n_tile * BN;
+
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's s_bias readers are done
+            for (int j = et; j < BN; j += 128) {
+                float v = 0.f;
+                const int n = n0 + j;
+                if (n < p.N) {
+                    if (p.bias) v += __half2float(p.bias[n]);
+                    if (p.rowvec) v += __half2float(p.rowvec[(size_t)b * p.rowvec_ld + n]);
+                }
+                s_bias[j] = v;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+
+            const int ph = h0 + et / p.tw, pw = w0 + et % p.tw;
+            const bool row_valid = (ph < p.img_h) && (pw < p.img_w);
+            const size_t pix = ((size_t)b * p.img_h + ph) * p.img_w + pw;
+            // pixel origin of this warp's 32-row store box
+            const int sh = h0 + (q * 32) / p.tw, sw = w0 + (q * 32) % p.tw;
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+
+#pragma unroll 1
+            for (int c = 0; c < BN / ACC_PER_CHUNK; ++c) {
+                const int nacc0 = n0 + c * ACC_PER_CHUNK;
+                if (nacc0 >= p.N) break;
+                uint32_t outp[16];
+                if constexpr (EPI == OMG_EPI_GEGLU) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_32x32(t_row + c * 64, r0);
+                    tmem_ld_32x32(t_row + c * 64 + 32, r1);
+                    tc_wait_ld();
+                    const float* sb = s_bias + c * 64;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float o[2];
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            const int i = 4 * j + 2 * t;  // column of the (value, gate) pair
+                            const float a = __uint_as_float(r0[i]) + sb[i];
+                            const float g = __uint_as_float(r0[i + 1]) + sb[i + 1];
+                            o[t] = a * gelu_erf(g);
+                        }
+                        outp[j] = pack_half2(o[0], o[1]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float o[2];
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            const int i = 4 * j + 2 * t;
+                            const float a = __uint_as_float(r1[i]) + sb[32 + i];
+                            const float g = __uint_as_float(r1[i + 1]) + sb[32 + i + 1];
+                            o[t] = a * gelu_erf(g);
+                        }
+                        outp[8 + j] = pack_half2(o[0], o[1]);
+                    }
+                } else {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_row + c * 32, r);
+                    tc_wait_ld();
+                    const float* sb = s_bias + c * 32;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sb[j];
+                    if (p.act_silu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
+                    }
+                    if (p.residual != nullptr && row_valid) {
+                        const uint4* rp =
+                            reinterpret_cast<const uint4*>(p.residual + pix * (size_t)p.residual_ld + nacc0);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const uint4 u = __ldg(rp + j4);
+                            const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float2 f = __half22float2(h2[t]);
+                                v[j4 * 8 + 2 * t] += f.x;
+                                v[j4 * 8 + 2 * t + 1] += f.y;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) outp[j] = pack_half2(v[2 * j], v[2 * j + 1]);
+                }
+                // staging buffer `buf` was last read by the TMA store issued two chunks ago
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
+                uint8_t* sbuf = my_stage + buf * 2048;
+                // 64 B rows, SWIZZLE_64B: 16 B chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int pj = j ^ ((lane >> 1) & 3);
+                    *reinterpret_cast<uint4*>(sbuf + lane * 64 + pj * 16) =
+                        make_uint4(outp[4 * j], outp[4 * j + 1], outp[4 * j + 2], outp[4 * j + 3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    const int nout0 = (EPI == OMG_EPI_GEGLU) ? (nacc0 >> 1) : nacc0;
+                    tma_store_4d(&p.d_map, sbuf, nout0, sw, sh, b);
+                    tma_store_commit();
+                }
+                buf ^= 1;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static int view_to_tmap(CUtensorMap* m, const omg_view4& v, uint32_t box_c, uint32_t box_w, uint32_t box_h,
+                        CUtensorMapSwizzle sw) {
+    const uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.W, (uint64_t)v.H, (uint64_t)v.B};
+    const uint64_t strides[4] = {1, (uint64_t)v.sw, (uint64_t)v.sh, (uint64_t)v.sb};
+    const uint32_t box[4] = {box_c, box_w, box_h, 1};
+    return make_tmap_f16(m, v.ptr, 4, dims, strides, box, sw);
+}
+
+template <int BN, int EPI>
+static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    static bool configured = false;
+    static int num_sms = 0;
+    if (!configured) {
+        OMG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::SMEM_BYTES));
+        int dev = 0;
+        OMG_CUDA(cudaGetDevice(&dev));
+        OMG_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        configured = true;
+    }
+    const int total = p.m_tiles * p.n_tiles;
+    const int grid = std::min(total, num_sms);
+    gemm_tc_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+    return check_launch("gemm_tc_kernel");
+}
+
+static int pick_block_n(int N, int epilogue, long m_tiles) {
+    if (epilogue == OMG_EPI_GEGLU) return 256;
+    // prefer exact division (no wasted columns), then fewer/larger tiles while keeping >= ~1.5 waves of work
+    const int cands[4] = {256, 160, 128, 64};
+    int best = 64;
+    double best_cost = 1e30;
+    for (int c : cands) {
+        const long nt = (N + c - 1) / c;
+        const long tiles = nt * m_tiles;
+        const long waves = (tiles + 147) / 148;
+        // cost ~ waves * per-tile time; small tiles are smem-bandwidth-bound (A tile re-read per 64 columns)
+        const double per_tile = (double)c + 64.0 * (c < 128 ? 1.0 : 0.25);
+        const double cost = (double)waves * per_tile;
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best = c;
+        }
+    }
+    return best;
+}
+
+}  // namespace omg
+
+using namespace omg;
+
+extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    OMG_CHECK(d != nullptr, "omg_gemm: null descriptor");
+    OMG_CHECK(d->n_a >= 1 && d->n_a <= OMG_MAX_A, "omg_gemm: n_a=%d out of range", d->n_a);
+    OMG_CHECK(d->n_segs >= 1 && d->n_segs <= OMG_MAX_SEGS, "omg_gemm: n_segs=%d out of range", d->n_segs);
+    OMG_CHECK(d->w && d->d.ptr, "omg_gemm: null weight/output pointer");
+    OMG_CHECK(d->N >= 8 && d->N % 8 == 0, "omg_gemm: N=%d must be a positive multiple of 8", d->N);
+    OMG_CHECK(d->Ktot % 8 == 0, "omg_gemm: Ktot=%d must be a multiple of 8", d->Ktot);
+    const bool geglu = d->epilogue == OMG_EPI_GEGLU;
+    const bool silu = d->epilogue == OMG_EPI_SILU;
+    OMG_CHECK(d->epilogue == OMG_EPI_NONE || geglu || silu, "omg_gemm: unknown epilogue %d", d->epilogue);
+    const int N_out = geglu ? d->N / 2 : d->N;
+    OMG_CHECK(d->d.C == N_out, "omg_gemm: output view has %d channels, expected %d", d->d.C, N_out);
+    OMG_CHECK(!geglu || (d->N % 64 == 0 && !d->residual && !d->rowvec),
+              "omg_gemm: GEGLU needs N %% 64 == 0 and no residual/rowvec");
+    OMG_CHECK(!d->residual || (N_out % 32 == 0 && d->residual_ld % 8 == 0),
+              "omg_gemm: residual needs N %% 32 == 0 and ld %% 8 == 0");
+
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    const int W = d->d.W, H = d->d.H, B = d->d.B;
+    OMG_CHECK(W >= 1 && H >= 1 && B >= 1, "omg_gemm: empty output grid");
+    int tw = 128;
+    while (tw / 2 >= W && tw > 1) tw /= 2;  // smallest power of two >= W, capped at 128
+    const int th = 128 / tw;
+    p.tw = tw;
+    p.th = th;
+    p.tiles_w = (W + tw - 1) / tw;
+    p.tiles_h = (H + th - 1) / th;
+    p.store_w = std::min(tw, 32);
+    p.store_h = 32 / p.store_w;
+    p.img_w = W;
+    p.img_h = H;
+    p.m_tiles = p.tiles_w * p.tiles_h * B;
+    p.N = d->N;
+    p.N_out = N_out;
+    int bn = d->block_n ? d->block_n : pick_block_n(d->N, d->epilogue, p.m_tiles);
+    OMG_CHECK(bn == 64 || bn == 128 || bn == 160 || bn == 256, "omg_gemm: block_n=%d unsupported", bn);
+    if (geglu) bn = 256;
+    p.n_tiles = (d->N + bn - 1) / bn;
+    p.bias = static_cast<const __half*>(d->bias);
+    p.rowvec = static_cast<const __half*>(d->rowvec);
+    p.rowvec_ld = d->rowvec_ld;
+    p.residual = static_cast<const __half*>(d->residual);
+    p.residual_ld = d->residual_ld;
+    p.act_silu = silu ? 1 : 0;
+
+    for (int i = 0; i < d->n_a; ++i) {
+        OMG_CHECK(d->a[i].ptr != nullptr, "omg_gemm: A view %d is null", i);
+        if (view_to_tmap(&p.a_maps[i], d->a[i], BK, tw, th, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    }
+    for (int i = d->n_a; i < OMG_MAX_A; ++i) p.a_maps[i] = p.a_maps[0];
+    {
+        const uint64_t dims[2] = {(uint64_t)d->Ktot, (uint64_t)d->N};
+        const uint64_t strides[2] = {1, (uint64_t)d->Ktot};
+        const uint32_t box[2] = {BK, (uint32_t)bn};
+        if (make_tmap_f16(&p.b_map, d->w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    }
+    if (view_to_tmap(&p.d_map, d->d, 32, p.store_w, p.store_h, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+
+    p.n_segs = d->n_segs;
+    for (int s = 0; s < d->n_segs; ++s) {
+        const omg_seg& sg = d->segs[s];
+        OMG_CHECK(sg.a_idx >= 0 && sg.a_idx < d->n_a, "omg_gemm: segment %d references A view %d", s, sg.a_idx);
+        OMG_CHECK(sg.k_len > 0 && sg.a_c0 >= 0 && sg.b_k0 >= 0 && sg.a_c0 + sg.k_len <= d->a[sg.a_idx].C,
+                  "omg_gemm: segment %d has a bad K range", s);
+        OMG_CHECK(sg.b_k0 + sg.k_len <= d->Ktot, "omg_gemm: segment %d exceeds weight K (%d + %d > %d)", s, sg.b_k0,
+                  sg.k_len, d->Ktot);
+        // A K-tail (k_len % 64 != 0) is only legal when the over-read of A is zero-filled, i.e. the segment ends
+        // at the end of the A view's channel range.
+        OMG_CHECK(sg.k_len % BK == 0 || sg.a_c0 + sg.k_len == d->a[sg.a_idx].C,
+                  "omg_gemm: segment %d: K tail must end at the A view's last channel", s);
+        p.segs[s] = SegDev{sg.a_idx, sg.dx, sg.dy, sg.a_c0, (sg.k_len + BK - 1) / BK, sg.b_k0};
+    }
+
+    if (geglu) return launch_gemm<256, OMG_EPI_GEGLU>(p, stream);
+    switch (bn) {
+        case 64: return launch_gemm<64, OMG_EPI_NONE>(p, stream);
+        case 128: return launch_gemm<128, OMG_EPI_NONE>(p, stream);
+        case 160: return launch_gemm<160, OMG_EPI_NONE>(p, stream);
+        default: return launch_gemm<256, OMG_EPI_NONE>(p, stream);
+    }
+}

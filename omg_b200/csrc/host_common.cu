@@ -1,0 +1,54 @@
+#include "host_common.h"
+
+#include <mutex>
+
+#include "../../include/omg_b200.h"
+
+namespace omg {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+int make_tmap_f16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                  const uint32_t* box, CUtensorMapSwizzle swizzle) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    OMG_CHECK(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        if (i > 0) {
+            gstr[i - 1] = strides_elems[i] * 2;  // bytes
+            OMG_CHECK(gstr[i - 1] % 16 == 0, "tensor map stride %d (%llu B) not a multiple of 16 B", i,
+                      (unsigned long long)gstr[i - 1]);
+        }
+        OMG_CHECK(box[i] >= 1 && box[i] <= 256, "tensor map box dim %d = %u out of range", i, box[i]);
+    }
+    OMG_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor map base pointer not 16 B aligned");
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bdim, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    OMG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+}  // namespace omg
+
+extern "C" const char* omg_last_error(void) { return omg::g_err; }
+extern "C" const char* omg_version(void) { return "omg_b200 0.1 sm_100a"; }
+extern "C" uint64_t omg_launch_count(void) { return omg::g_launches.load(); }

@@ -1,0 +1,54 @@
+// Host-side helpers shared by the C-ABI entry points: error string, launch counter, TMA descriptor encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+namespace omg {
+
+extern thread_local char g_err[512];
+extern std::atomic<uint64_t> g_launches;
+
+inline int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+#define OMG_CHECK(cond, ...) \
+    do {                     \
+        if (!(cond)) return ::omg::fail(__VA_ARGS__); \
+    } while (0)
+
+#define OMG_CUDA(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) return ::omg::fail("%s failed: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("launch of %s failed: %s", what, cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// libcuda is resolved at run time through the runtime (the build box has no driver library to link against).
+PFN_encodeTiled get_encode_tiled();
+
+// fp16 tensor map of rank `rank` (<=5). dims[0] is the contiguous dimension. strides are in ELEMENTS for
+// dims[1..rank-1].  Out-of-bounds box elements read as zero / are clipped on store.
+int make_tmap_f16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                  const uint32_t* box, CUtensorMapSwizzle swizzle);
+
+}  // namespace omg

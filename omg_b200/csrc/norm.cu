@@ -1,0 +1,248 @@
+// GroupNorm(32) [+SiLU] and LayerNorm over channels-last fp16 activations.  HBM-bound: each element is read
+// twice (statistics, apply) and written once; algorithmic bytes per launch pair = 3 * B*HW*C * 2 B.
+//
+// GroupNorm reads from up to two sources that are concatenated along channels (the UNet decoder's
+// cat([hidden, skip], dim=1), diffusers UNet2DConditionModel up-blocks [3P]); the concatenation is never
+// materialised un-normalised: the apply pass writes the normalised, activated, concatenated tensor that the
+// following conv consumes through TMA.
+#include <cuda_fp16.h>
+
+#include "../../include/omg_b200.h"
+#include "host_common.h"
+
+namespace omg {
+
+struct GnSrc {
+    const __half* x1;
+    const __half* x2;
+    int C1, C2;  // channels of each source (C2 = 0 when unused); both multiples of 8
+};
+
+__device__ __forceinline__ uint4 gn_load8(const GnSrc& s, size_t pix, int c) {
+    // c is a multiple of 8 and an 8-vector never straddles the two sources
+    if (c < s.C1) return *reinterpret_cast<const uint4*>(s.x1 + pix * s.C1 + c);
+    return *reinterpret_cast<const uint4*>(s.x2 + pix * s.C2 + (c - s.C1));
+}
+
+// stats[b][g] = {sum, sumsq}.  grid = (row_splits, B); block = (C/8, rows_par)
+__global__ void gn_stats_kernel(GnSrc s, int HW, int cpg, int rows_per_cta, float* __restrict__ stats) {
+    __shared__ float s_sum[32], s_sq[32];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid < 32) {
+        s_sum[tid] = 0.f;
+        s_sq[tid] = 0.f;
+    }
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int c = threadIdx.x * 8;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(r0 + rows_per_cta, HW);
+    float a[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = q[i] = 0.f;
+    for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+        const uint4 u = gn_load8(s, (size_t)b * HW + r, c);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h2[i]);
+            a[2 * i] += f.x;
+            q[2 * i] += f.x * f.x;
+            a[2 * i + 1] += f.y;
+            q[2 * i + 1] += f.y * f.y;
+        }
+    }
+    // fold the 8 channels into (at most two) groups, then into the CTA accumulators
+    int g_prev = c / cpg;
+    float ps = 0.f, pq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int g = (c + i) / cpg;
+        if (g != g_prev) {
+            atomicAdd(&s_sum[g_prev], ps);
+            atomicAdd(&s_sq[g_prev], pq);
+            ps = pq = 0.f;
+            g_prev = g;
+        }
+        ps += a[i];
+        pq += q[i];
+    }
+    atomicAdd(&s_sum[g_prev], ps);
+    atomicAdd(&s_sq[g_prev], pq);
+    __syncthreads();
+    if (tid < 32) {
+        atomicAdd(&stats[((size_t)b * 32 + tid) * 2], s_sum[tid]);
+        atomicAdd(&stats[((size_t)b * 32 + tid) * 2 + 1], s_sq[tid]);
+    }
+}
+
+// grid = (ceil(HW*C/8 / 256), B)
+__global__ void gn_apply_kernel(GnSrc s, int HW, int cpg, float eps, int silu, const float* __restrict__ stats,
+                                const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                                __half* __restrict__ y) {
+    const int C = s.C1 + s.C2;
+    const int vec_per_row = C / 8;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)HW * vec_per_row) return;
+    const int b = blockIdx.y;
+    const size_t r = idx / vec_per_row;
+    const int c = (int)(idx % vec_per_row) * 8;
+    const uint4 u = gn_load8(s, (size_t)b * HW + r, c);
+    const uint4 gw = *reinterpret_cast<const uint4*>(gamma + c);
+    const uint4 bw = *reinterpret_cast<const uint4*>(beta + c);
+    const __half* xh = reinterpret_cast<const __half*>(&u);
+    const __half* gh = reinterpret_cast<const __half*>(&gw);
+    const __half* bh = reinterpret_cast<const __half*>(&bw);
+    const float inv_n = 1.0f / ((float)HW * (float)cpg);
+    float out[8];
+    int g_cur = -1;
+    float mean = 0.f, rstd = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int g = (c + i) / cpg;
+        if (g != g_cur) {
+            g_cur = g;
+            const float sm = stats[((size_t)b * 32 + g) * 2], sq = stats[((size_t)b * 32 + g) * 2 + 1];
+            mean = sm * inv_n;
+            const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
+            rstd = rsqrtf(var + eps);
+        }
+        float v = (__half2float(xh[i]) - mean) * rstd * __half2float(gh[i]) + __half2float(bh[i]);
+        if (silu) v = v / (1.0f + __expf(-v));
+        out[i] = v;
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(out[2 * i], out[2 * i + 1]);
+    *reinterpret_cast<uint4*>(y + ((size_t)b * HW + r) * C + c) = o;
+}
+
+// One warp per token row; exact two-pass variance held in registers (C <= 2560).
+template <int MAX_VEC>
+__global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
+                                 const __half* __restrict__ beta, __half* __restrict__ y, long long rows, int C,
+                                 float eps) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int nvec = C / 8;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+    float v[MAX_VEC][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAX_VEC; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < nvec) {
+            const uint4 u = xr[vi];
+            const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(h2[i]);
+                v[k][2 * i] = f.x;
+                v[k][2 * i + 1] = f.y;
+                sum += f.x + f.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAX_VEC; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < nvec) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float d = v[k][i] - mean;
+                sq += d * d;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)C + eps);
+    uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll
+    for (int k = 0; k < MAX_VEC; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < nvec) {
+            const uint4 gw = reinterpret_cast<const uint4*>(gamma)[vi];
+            const uint4 bw = reinterpret_cast<const uint4*>(beta)[vi];
+            const __half2* g2 = reinterpret_cast<const __half2*>(&gw);
+            const __half2* b2 = reinterpret_cast<const __half2*>(&bw);
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 gf = __half22float2(g2[i]);
+                const float2 bf = __half22float2(b2[i]);
+                oh[i] = __floats2half2_rn((v[k][2 * i] - mean) * rstd * gf.x + bf.x,
+                                          (v[k][2 * i + 1] - mean) * rstd * gf.y + bf.y);
+            }
+            yr[vi] = o;
+        }
+    }
+}
+
+}  // namespace omg
+
+using namespace omg;
+
+extern "C" int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, const void* gamma,
+                             const void* beta, float eps, int silu, void* stats_ws, void* y, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    const int C = C1 + C2;
+    OMG_CHECK(x1 && gamma && beta && stats_ws && y, "omg_groupnorm: null pointer");
+    OMG_CHECK(C1 > 0 && C1 % 8 == 0 && C2 >= 0 && C2 % 8 == 0 && (C2 == 0 || x2), "omg_groupnorm: bad channel split");
+    OMG_CHECK(C % 32 == 0 && C / 8 <= 1024, "omg_groupnorm: C=%d must be a multiple of 32 and <= 8192", C);
+    OMG_CHECK(B >= 1 && HW >= 1, "omg_groupnorm: empty input");
+    const int cpg = C / 32;
+    GnSrc s{static_cast<const __half*>(x1), static_cast<const __half*>(x2), C1, C2};
+    OMG_CUDA(cudaMemsetAsync(stats_ws, 0, (size_t)B * 32 * 2 * sizeof(float), stream));
+    const int tx = C / 8;
+    int ty = 1024 / tx;
+    if (ty > 16) ty = 16;
+    if (ty < 1) ty = 1;
+    // enough CTAs to fill the machine: ~4 per SM across the batch
+    int splits = (148 * 4 + B - 1) / B;
+    int rows_per_cta = (HW + splits - 1) / splits;
+    if (rows_per_cta < ty) rows_per_cta = ty;
+    splits = (HW + rows_per_cta - 1) / rows_per_cta;
+    gn_stats_kernel<<<dim3(splits, B), dim3(tx, ty), 0, stream>>>(s, HW, cpg, rows_per_cta,
+                                                                   static_cast<float*>(stats_ws));
+    if (check_launch("gn_stats_kernel")) return 1;
+    const size_t nvec = (size_t)HW * (C / 8);
+    gn_apply_kernel<<<dim3((unsigned)((nvec + 255) / 256), B), 256, 0, stream>>>(
+        s, HW, cpg, eps, silu, static_cast<const float*>(stats_ws), static_cast<const __half*>(gamma),
+        static_cast<const __half*>(beta), static_cast<__half*>(y));
+    return check_launch("gn_apply_kernel");
+}
+
+extern "C" int omg_layernorm(const void* x, const void* gamma, const void* beta, void* y, long long rows, int C,
+                             float eps, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    OMG_CHECK(x && gamma && beta && y, "omg_layernorm: null pointer");
+    OMG_CHECK(C % 8 == 0 && C >= 8 && C <= 2560, "omg_layernorm: C=%d unsupported", C);
+    OMG_CHECK(rows >= 1, "omg_layernorm: empty input");
+    const int warps = 8;
+    const unsigned grid = (unsigned)((rows + warps - 1) / warps);
+    const int nvec = C / 8;
+    if (nvec <= 96)
+        layernorm_kernel<3><<<grid, warps * 32, 0, stream>>>(static_cast<const __half*>(x),
+                                                             static_cast<const __half*>(gamma),
+                                                             static_cast<const __half*>(beta),
+                                                             static_cast<__half*>(y), rows, C, eps);
+    else if (nvec <= 160)
+        layernorm_kernel<5><<<grid, warps * 32, 0, stream>>>(static_cast<const __half*>(x),
+                                                             static_cast<const __half*>(gamma),
+                                                             static_cast<const __half*>(beta),
+                                                             static_cast<__half*>(y), rows, C, eps);
+    else
+        layernorm_kernel<10><<<grid, warps * 32, 0, stream>>>(static_cast<const __half*>(x),
+                                                              static_cast<const __half*>(gamma),
+                                                              static_cast<const __half*>(beta),
+                                                              static_cast<__half*>(y), rows, C, eps);
+    return check_launch("layernorm_kernel");
+}

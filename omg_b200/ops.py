@@ -1,0 +1,228 @@
+"""Host-side launchers: torch tensors (device memory + stream plumbing only) -> C-ABI descriptors.
+
+All activations are channels-last fp16: (B, H, W, C), equivalently (B, H*W tokens, C).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk16(t: torch.Tensor):
+    if not t.is_cuda or t.dtype != torch.float16:
+        raise ValueError("expected a CUDA fp16 tensor (there is no CPU path)")
+
+
+def view4(t: torch.Tensor) -> L.View4:
+    """(B,H,W,C) tensor (any pixel strides, unit channel stride) or 2-D [M,K] matrix -> omg_view4."""
+    _chk16(t)
+    if t.dim() == 2:
+        assert t.stride(1) == 1
+        return L.View4(t.data_ptr(), t.shape[1], t.shape[0], 1, 1, t.stride(0), t.stride(0) * t.shape[0],
+                       t.stride(0) * t.shape[0])
+    assert t.dim() == 4 and t.stride(3) == 1
+    B, H, W, Cc = t.shape
+    return L.View4(t.data_ptr(), Cc, W, H, B, t.stride(2), t.stride(1), t.stride(0))
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def gemm(a_views, segs, w, N, Ktot, d_view, bias=None, rowvec=None, rowvec_ld=0, residual=None, residual_ld=0,
+         epilogue=L.EPI_NONE, block_n=0):
+    d = L.GemmDesc()
+    d.n_a = len(a_views)
+    for i, v in enumerate(a_views):
+        d.a[i] = v
+    d.n_segs = len(segs)
+    for i, s in enumerate(segs):
+        d.segs[i] = L.Seg(*s)
+    d.w = w.data_ptr()
+    d.N, d.Ktot = N, Ktot
+    d.d = d_view
+    d.bias = _ptr(bias)
+    d.rowvec = _ptr(rowvec)
+    d.rowvec_ld = rowvec_ld
+    d.residual = _ptr(residual)
+    d.residual_ld = residual_ld
+    d.epilogue = epilogue
+    d.block_n = block_n
+    L.check(L.load().omg_gemm(C.byref(d), _stream()), "omg_gemm")
+
+
+def linear(x, w, bias=None, residual=None, out=None, epilogue=L.EPI_NONE, extra=None, block_n=0):
+    """out[M, N'] = epi(x[M,K] @ w[N, :K]^T (+ sum_i extra_i.x[M,Ki] @ w[N, off_i:off_i+Ki]^T) + bias) + residual.
+
+    `extra` = list of (tensor [M,Ki], weight column offset): further K-segments (LoRA deltas  s*B(Ax)).
+    """
+    _chk16(x)
+    M, K = x.shape
+    N, Ktot = w.shape
+    n_out = N // 2 if epilogue == L.EPI_GEGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.float16, device=x.device)
+    views = [view4(x)]
+    segs = [(0, 0, 0, 0, K, 0)]
+    for t, off in (extra or []):
+        views.append(view4(t))
+        segs.append((len(views) - 1, 0, 0, 0, t.shape[1], off))
+    gemm(views, segs, w, N, Ktot, view4(out), bias=bias, residual=residual,
+         residual_ld=0 if residual is None else residual.stride(0), epilogue=epilogue, block_n=block_n)
+    return out
+
+
+def _taps3x3(Cin, a_idx=0, c0=0, k0=0):
+    return [(a_idx, kx - 1, ky - 1, c0, Cin, k0 + (ky * 3 + kx) * Cin) for ky in range(3) for kx in range(3)]
+
+
+def conv3x3(x, w, bias=None, rowvec=None, residual=None, out=None, shortcut=None, block_n=0):
+    """3x3 / stride 1 / pad 1 conv over (B,H,W,Cin).  w = [N, 9*Cin (+ shortcut K)] packed (ky, kx, c).
+
+    shortcut = list of (tensor (B,H,W,Ci), weight column offset): 1x1-conv K-segments added to the same accumulator
+    (ResnetBlock2D conv_shortcut).  rowvec [B, N] is added per image (time-embedding projection).
+    """
+    B, H, W, Cin = x.shape
+    N, Ktot = w.shape
+    if out is None:
+        out = torch.empty((B, H, W, N), dtype=torch.float16, device=x.device)
+    views = [view4(x)]
+    segs = _taps3x3(Cin)
+    for t, off in (shortcut or []):
+        views.append(view4(t))
+        segs.append((len(views) - 1, 0, 0, 0, t.shape[3], off))
+    gemm(views, segs, w, N, Ktot, view4(out), bias=bias, rowvec=rowvec,
+         rowvec_ld=0 if rowvec is None else rowvec.stride(0),
+         residual=residual, residual_ld=0 if residual is None else N, block_n=block_n)
+    return out
+
+
+def conv3x3_s2(x, w, bias=None, out=None, block_n=0):
+    """3x3 / stride 2 / pad 1 conv (Downsample2D): A operands are the four stride-2 phase views of x."""
+    B, H, W, Cin = x.shape
+    N, Ktot = w.shape
+    assert H % 2 == 0 and W % 2 == 0
+    if out is None:
+        out = torch.empty((B, H // 2, W // 2, N), dtype=torch.float16, device=x.device)
+    views = [view4(x[:, py::2, px::2, :]) for py in range(2) for px in range(2)]
+    segs = []
+    for ky in range(3):
+        for kx in range(3):
+            py, oy = (1, -1) if ky == 0 else ((0, 0) if ky == 1 else (1, 0))
+            px, ox = (1, -1) if kx == 0 else ((0, 0) if kx == 1 else (1, 0))
+            segs.append((py * 2 + px, ox, oy, 0, Cin, (ky * 3 + kx) * Cin))
+    gemm(views, segs, w, N, Ktot, view4(out), bias=bias, block_n=block_n)
+    return out
+
+
+def upsample2x_conv3x3(x, w, bias=None, out=None, block_n=0):
+    """nearest-2x upsample followed by 3x3 conv (Upsample2D) without materialising the upsampled tensor:
+    each output phase (py,px) is a 9-tap conv over x with shifted taps, stored through a strided output view."""
+    B, H, W, Cin = x.shape
+    N, Ktot = w.shape
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, N), dtype=torch.float16, device=x.device)
+    xv = view4(x)
+    off = {0: (-1, 0, 0), 1: (0, 0, 1)}
+    for py in range(2):
+        for px in range(2):
+            segs = [(0, off[px][kx], off[py][ky], 0, Cin, (ky * 3 + kx) * Cin) for ky in range(3) for kx in range(3)]
+            gemm([xv], segs, w, N, Ktot, view4(out[:, py::2, px::2, :]), bias=bias, block_n=block_n)
+    return out
+
+
+def attention(q, k, v, out, heads, n_q, n_kv, items, q_col0=0, k_col0=0, v_col0=0, out_col0=0, scale=0.125,
+              out_weight=1.0, accumulate=False):
+    """q/k/v/out: [batch, tokens, ld] fp16.  items: list of (out_b, q_b, k_b, v_b)."""
+    for t in (q, k, v, out):
+        _chk16(t)
+        assert t.dim() == 3 and t.stride(2) == 1
+    d = L.AttnDesc()
+    d.q, d.q_ld, d.q_bs, d.q_col0 = q.data_ptr(), q.stride(1), q.stride(0), q_col0
+    d.k, d.k_ld, d.k_bs, d.k_col0 = k.data_ptr(), k.stride(1), k.stride(0), k_col0
+    d.v, d.v_ld, d.v_bs, d.v_col0 = v.data_ptr(), v.stride(1), v.stride(0), v_col0
+    d.out, d.out_ld, d.out_bs, d.out_col0 = out.data_ptr(), out.stride(1), out.stride(0), out_col0
+    d.n_q, d.n_kv, d.heads, d.head_dim = n_q, n_kv, heads, 64
+    d.n_items = len(items)
+    for i, (ob, qb, kb, vb) in enumerate(items):
+        d.out_b[i], d.q_b[i], d.k_b[i], d.v_b[i] = ob, qb, kb, vb
+    d.scale, d.out_weight, d.accumulate = scale, out_weight, int(accumulate)
+    L.check(L.load().omg_attention(C.byref(d), _stream()), "omg_attention")
+    return out
+
+
+def groupnorm(x1, gamma, beta, eps, silu, x2=None, out=None, stats_ws=None):
+    """GroupNorm(32)(cat([x1, x2], channel)) [+ SiLU]; x: (B, H, W, C) or (B, HW, C)."""
+    _chk16(x1)
+    B = x1.shape[0]
+    C1 = x1.shape[-1]
+    HW = x1.numel() // (B * C1)
+    C2 = 0 if x2 is None else x2.shape[-1]
+    assert x1.is_contiguous() and (x2 is None or x2.is_contiguous())
+    if out is None:
+        out = torch.empty((*x1.shape[:-1], C1 + C2), dtype=torch.float16, device=x1.device)
+    if stats_ws is None:
+        stats_ws = torch.empty(B * 64, dtype=torch.float32, device=x1.device)
+    L.check(L.load().omg_groupnorm(x1.data_ptr(), C1, _ptr(x2), C2, B, HW, gamma.data_ptr(), beta.data_ptr(),
+                                   float(eps), int(silu), stats_ws.data_ptr(), out.data_ptr(), _stream()),
+            "omg_groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    _chk16(x)
+    assert x.is_contiguous()
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    if out is None:
+        out = torch.empty_like(x)
+    L.check(L.load().omg_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows, Cc,
+                                   float(eps), _stream()), "omg_layernorm")
+    return out
+
+
+def fuse_step(noise_main, noise_concepts, masks, guidance, sigma, sigma_next, latents, next_main_in=None,
+              next_concept_in=None, latents_f16=None):
+    d = L.FuseDesc()
+    d.noise_main = noise_main.data_ptr()
+    d.n_concepts = len(noise_concepts)
+    for i, (n, m) in enumerate(zip(noise_concepts, masks)):
+        d.noise_concept[i] = _ptr(n)
+        d.mask[i] = _ptr(m)
+    d.guidance, d.sigma, d.sigma_next = float(guidance), float(sigma), float(sigma_next)
+    d.latents = latents.data_ptr()
+    d.next_main_in = _ptr(next_main_in)
+    d.next_concept_in = _ptr(next_concept_in)
+    d.latents_f16 = _ptr(latents_f16)
+    d.HW = latents.shape[1] * latents.shape[2] if latents.dim() == 4 else latents.shape[1]
+    L.check(L.load().omg_fuse_step(C.byref(d), _stream()), "omg_fuse_step")
+
+
+def ctx_mix(ctx, coef, out=None):
+    _chk16(ctx)
+    B, Lk, Cc = ctx.shape
+    if out is None:
+        out = torch.empty_like(ctx)
+    L.check(L.load().omg_ctx_mix(ctx.data_ptr(), coef.data_ptr(), out.data_ptr(), B, Lk, Cc, _stream()),
+            "omg_ctx_mix")
+    return out
+
+
+# ------------------------------------------------------------------ weight packing (host, once per model load)
+def pack_conv3x3_weight(w):
+    """torch Conv2d weight [N, C, 3, 3] -> [N, 9*C] with K order (ky, kx, c)."""
+    N, Cc = w.shape[:2]
+    return w.permute(0, 2, 3, 1).reshape(N, 9 * Cc).contiguous()
+
+
+def pack_geglu_weight(w, b=None):
+    """GEGLU proj Linear(c -> 8c): rows [value(4c) ; gate(4c)] -> interleaved (value_j, gate_j)."""
+    n2 = w.shape[0] // 2
+    wi = torch.stack([w[:n2], w[n2:]], dim=1).reshape(w.shape[0], w.shape[1]).contiguous()
+    bi = None if b is None else torch.stack([b[:n2], b[n2:]], dim=1).reshape(-1).contiguous()
+    return wi, bi

@@ -1,0 +1,246 @@
+"""GPU parity of each hand-written kernel (through the C ABI) against a plain fp32 torch restatement of the same
+op on the same fp16 inputs.  Tolerances: relative L2 <= 2e-3 (fp16 storage of the result, fp32 accumulation)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).half()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from omg_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(256, 256, 128, 0), (4096, 1280, 1280, 0), (1000, 640, 320, 0),
+                                      (308, 2560, 2048, 0), (4, 1280, 2816, 0), (512, 320, 960, 160),
+                                      (512, 320, 960, 64), (2048, 1920, 640, 128), (2048, 1280, 640, 256)])
+def test_linear(ops, M, N, K, bn):
+    x, w, b = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2), rnd(N, seed=3)
+    r = rnd(M, N, seed=4)
+    out = ops.linear(x, w, bias=b, residual=r, block_n=bn)
+    ref = x.float() @ w.float().t() + b.float() + r.float()
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 2e-3
+
+
+def test_linear_silu_and_lora(ops):
+    M, N, K, R = 1024, 640, 640, 32
+    x, w = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2)
+    a, bw = rnd(R, K, scale=K ** -0.5, seed=3), rnd(N, R, scale=0.1 * R ** -0.5, seed=4)
+    t = ops.linear(x, a)  # t = A x   [M, R]
+    wcat = torch.cat([w, 0.8 * bw], dim=1).contiguous()  # [N, K + R]
+    out = ops.linear(x, wcat, extra=[(t, K)])
+    ref = x.float() @ w.float().t() + (t.float() @ (0.8 * bw).float().t())
+    assert rel(out, ref) < 2e-3
+    out2 = ops.linear(x, w, epilogue=2)
+    assert rel(out2, F.silu(x.float() @ w.float().t())) < 2e-3
+
+
+def test_geglu(ops):
+    M, C = 1024, 640
+    x = rnd(M, C, seed=1)
+    w, b = rnd(8 * C, C, scale=C ** -0.5, seed=2), rnd(8 * C, seed=3)
+    wi, bi = ops.pack_geglu_weight(w, b)
+    out = ops.linear(x, wi, bias=bi, epilogue=1)
+    h = x.float() @ w.float().t() + b.float()
+    ref = h[:, :4 * C] * F.gelu(h[:, 4 * C:])
+    assert out.shape == (M, 4 * C)
+    assert rel(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,N", [(2, 32, 32, 128, 256), (1, 64, 64, 320, 320), (2, 16, 16, 640, 1280),
+                                         (1, 128, 128, 64, 128), (1, 24, 40, 64, 64)])
+def test_conv3x3(ops, B, H, W, Cin, N):
+    x = rnd(B, H, W, Cin, seed=1)
+    w = rnd(N, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    b = rnd(N, seed=3)
+    temb = rnd(B, N, seed=4)
+    out = ops.conv3x3(x, ops.pack_conv3x3_weight(w), bias=b, rowvec=temb)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=1) + temb.float()[:, :, None, None]
+    assert rel(out.permute(0, 3, 1, 2), ref) < 2e-3
+
+
+def test_conv3x3_shortcut_residual(ops):
+    B, H, W, C1, C2, N = 2, 32, 32, 128, 64, 256
+    h = rnd(B, H, W, N, seed=1)
+    xa, xb = rnd(B, H, W, C1, seed=2), rnd(B, H, W, C2, seed=3)
+    w = rnd(N, N, 3, 3, scale=(9 * N) ** -0.5, seed=4)
+    ws = rnd(N, C1 + C2, scale=(C1 + C2) ** -0.5, seed=5)
+    b = rnd(N, seed=6)
+    wcat = torch.cat([ops.pack_conv3x3_weight(w), ws], dim=1).contiguous()
+    out = ops.conv3x3(h, wcat, bias=b, shortcut=[(xa, 9 * N), (xb, 9 * N + C1)])
+    x = torch.cat([xa, xb], dim=3).float().permute(0, 3, 1, 2)
+    ref = F.conv2d(h.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=1) + \
+        F.conv2d(x, ws.float()[:, :, None, None])
+    assert rel(out.permute(0, 3, 1, 2), ref) < 2e-3
+    # identity shortcut as residual
+    r = rnd(B, H, W, N, seed=7)
+    out2 = ops.conv3x3(h, ops.pack_conv3x3_weight(w), bias=b, residual=r)
+    ref2 = F.conv2d(h.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=1) + r.float().permute(0, 3, 1, 2)
+    assert rel(out2.permute(0, 3, 1, 2), ref2) < 2e-3
+
+
+def test_conv_small_channels(ops):
+    # conv_in (4 -> 320, stored as 8 channels) and conv_out (320 -> 4, stored as 8)
+    B, H, W = 2, 32, 32
+    x = torch.zeros(B, H, W, 8, device="cuda", dtype=torch.float16)
+    x[..., :4] = rnd(B, H, W, 4, seed=1)
+    w = rnd(320, 4, 3, 3, scale=36 ** -0.5, seed=2)
+    w8 = torch.zeros(320, 8, 3, 3, device="cuda", dtype=torch.float16)
+    w8[:, :4] = w
+    out = ops.conv3x3(x, ops.pack_conv3x3_weight(w8))
+    ref = F.conv2d(x[..., :4].float().permute(0, 3, 1, 2), w.float(), padding=1)
+    assert rel(out.permute(0, 3, 1, 2), ref) < 2e-3
+    y = rnd(B, H, W, 320, seed=3)
+    wo = rnd(4, 320, 3, 3, scale=2880 ** -0.5, seed=4)
+    wo8 = torch.zeros(8, 320, 3, 3, device="cuda", dtype=torch.float16)
+    wo8[:4] = wo
+    out = ops.conv3x3(y, ops.pack_conv3x3_weight(wo8))
+    ref = F.conv2d(y.float().permute(0, 3, 1, 2), wo.float(), padding=1)
+    assert rel(out[..., :4].permute(0, 3, 1, 2), ref) < 2e-3
+    assert out[..., 4:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 128), (1, 64, 64, 320)])
+def test_conv_down_up(ops, B, H, W, C):
+    x = rnd(B, H, W, C, seed=1)
+    w = rnd(C, C, 3, 3, scale=(9 * C) ** -0.5, seed=2)
+    b = rnd(C, seed=3)
+    wp = ops.pack_conv3x3_weight(w)
+    xn = x.float().permute(0, 3, 1, 2)
+    out = ops.conv3x3_s2(x, wp, bias=b)
+    ref = F.conv2d(xn, w.float(), b.float(), stride=2, padding=1)
+    assert rel(out.permute(0, 3, 1, 2), ref) < 2e-3
+    out = ops.upsample2x_conv3x3(x, wp, bias=b)
+    ref = F.conv2d(F.interpolate(xn, scale_factor=2.0, mode="nearest"), w.float(), b.float(), padding=1)
+    assert rel(out.permute(0, 3, 1, 2), ref) < 2e-3
+
+
+def _attn_ref(q, k, v, heads, scale):
+    B, Nq, Cc = q.shape
+    d = Cc // heads
+    qh = q.float().view(B, Nq, heads, d).transpose(1, 2)
+    kh = k.float().view(B, -1, heads, d).transpose(1, 2)
+    vh = v.float().view(B, -1, heads, d).transpose(1, 2)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+    return (p @ vh).transpose(1, 2).reshape(B, Nq, Cc)
+
+
+@pytest.mark.parametrize("B,N,heads", [(2, 1024, 10), (1, 4096, 5), (2, 256, 20), (1, 384, 2)])
+def test_self_attention(ops, B, N, heads):
+    Cc = heads * 64
+    qkv = rnd(B, N, 3 * Cc, seed=1)
+    out = torch.empty(B, N, Cc, device="cuda", dtype=torch.float16)
+    items = [(b, b, b, b) for b in range(B)]
+    ops.attention(qkv, qkv, qkv, out, heads, N, N, items, q_col0=0, k_col0=Cc, v_col0=2 * Cc)
+    ref = _attn_ref(qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:], heads, 0.125)
+    assert rel(out, ref) < 2e-3
+
+
+def test_attention_p2p_remap_and_cross(ops):
+    B, N, heads, Lk = 4, 1024, 10, 77
+    Cc = heads * 64
+    qkv = rnd(B, N, 3 * Cc, seed=1)
+    out = torch.empty(B, N, Cc, device="cuda", dtype=torch.float16)
+    # rows (u0,u1,c0,c1): c1 takes Q,K from c0 and V from itself (replace_self_attention)
+    items = [(0, 0, 0, 0), (1, 1, 1, 1), (2, 2, 2, 2), (3, 2, 2, 3)]
+    ops.attention(qkv, qkv, qkv, out, heads, N, N, items, q_col0=0, k_col0=Cc, v_col0=2 * Cc)
+    q, k, v = qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:]
+    ref = _attn_ref(q[[0, 1, 2, 2]], k[[0, 1, 2, 2]], v, heads, 0.125)
+    assert rel(out, ref) < 2e-3
+    # cross attention: 77 text keys + 16 image keys, decoupled: txt + 0.8 * ip
+    qx = rnd(B, N, Cc, seed=2)
+    kv = rnd(B, Lk, 2 * Cc, seed=3)
+    kvip = rnd(B, 16, 2 * Cc, seed=4)
+    it = [(b, b, b, b) for b in range(B)]
+    ops.attention(qx, kv, kv, out, heads, N, Lk, it, k_col0=0, v_col0=Cc)
+    ref_t = _attn_ref(qx, kv[..., :Cc], kv[..., Cc:], heads, 0.125)
+    assert rel(out, ref_t) < 2e-3
+    ops.attention(qx, kvip, kvip, out, heads, N, 16, it, k_col0=0, v_col0=Cc, out_weight=0.8, accumulate=True)
+    ref_ip = _attn_ref(qx, kvip[..., :Cc], kvip[..., Cc:], heads, 0.125)
+    assert rel(out, ref_t + 0.8 * ref_ip) < 2e-3
+
+
+@pytest.mark.parametrize("B,HW,C1,C2,silu", [(2, 1024, 320, 0, 1), (2, 4096, 640, 320, 1), (1, 256, 1280, 1280, 1),
+                                             (3, 1024, 640, 0, 0)])
+def test_groupnorm(ops, B, HW, C1, C2, silu):
+    x1 = rnd(B, HW, C1, seed=1) + 0.5
+    x2 = rnd(B, HW, C2, scale=2.0, seed=2) if C2 else None
+    Cc = C1 + C2
+    g, b = rnd(Cc, seed=3) + 1, rnd(Cc, seed=4)
+    out = ops.groupnorm(x1, g, b, 1e-5, silu, x2=x2)
+    x = x1 if x2 is None else torch.cat([x1, x2], dim=2)
+    ref = F.group_norm(x.float().transpose(1, 2), 32, g.float(), b.float(), 1e-5).transpose(1, 2)
+    if silu:
+        ref = F.silu(ref)
+    assert rel(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("rows,C", [(4096, 640), (1000, 1280), (77, 2048)])
+def test_layernorm(ops, rows, C):
+    x = rnd(rows, C, seed=1) * 3 + 1
+    g, b = rnd(C, seed=2) + 1, rnd(C, seed=3)
+    out = ops.layernorm(x, g, b)
+    ref = F.layer_norm(x.float(), (C,), g.float(), b.float(), 1e-5)
+    assert rel(out, ref) < 2e-3
+
+
+def test_fuse_step(ops):
+    H = W = 64
+    HW = H * W
+    g = torch.Generator(device="cuda").manual_seed(0)
+    nm = torch.zeros(4, HW, 8, device="cuda", dtype=torch.float16)
+    nm[..., :4] = torch.randn(4, HW, 4, generator=g, device="cuda").half()
+    ncs, masks = [], []
+    for k in range(2):
+        n = torch.zeros(2, HW, 8, device="cuda", dtype=torch.float16)
+        n[..., :4] = torch.randn(2, HW, 4, generator=g, device="cuda").half()
+        ncs.append(n)
+        m = torch.zeros(H, W, device="cuda")
+        m[8:40, 4 + 20 * k:36 + 20 * k] = 1.0  # overlapping rectangles
+        masks.append(m.reshape(-1).contiguous())
+    lat = torch.randn(2, HW, 4, generator=g, device="cuda") * 10
+    lat0 = lat.clone()
+    nxt = torch.empty(4, HW, 8, device="cuda", dtype=torch.float16)
+    nxc = torch.empty(2, HW, 8, device="cuda", dtype=torch.float16)
+    sig, sign, gs = 5.0, 4.2, 7.5
+    ops.fuse_step(nm, ncs, masks, gs, sig, sign, lat, nxt, nxc)
+    # restatement of lora_pipeline.py:568-615
+    noise = nm[..., :4].float()
+    U = ((masks[0] == 1) | (masks[1] == 1)).float()[None, :, None]
+    edit = torch.stack([noise[1], noise[3]])
+    new = edit * (1 - U)
+    for k in range(2):
+        new = new + ncs[k][..., :4].float() * masks[k][None, :, None]
+    noise = noise.clone()
+    noise[1], noise[3] = new[0], new[1]
+    eps = noise[:2] + gs * (noise[2:] - noise[:2])
+    ref = lat0 + eps * (sign - sig)
+    assert rel(lat, ref) < 1e-6
+    sc = ref / math.sqrt(sign * sign + 1)
+    assert rel(nxt[..., :4], torch.cat([sc, sc])) < 1e-3
+    assert rel(nxc[..., :4], torch.stack([sc[1], sc[1]])) < 1e-3
+    assert nxt[..., 4:].abs().max().item() == 0
+
+
+def test_ctx_mix(ops):
+    ctx = rnd(2, 77, 2048, seed=1)
+    coef = torch.rand(77, 77, device="cuda")
+    out = ops.ctx_mix(ctx, coef)
+    ref = torch.einsum("wn,bnc->bwc", coef, ctx.float())
+    assert rel(out, ref) < 2e-3
