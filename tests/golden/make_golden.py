@@ -1,0 +1,149 @@
+"""Generate golden vectors from the UNMODIFIED reference modules that are importable in the build container
+(/root/reference is not present on the GPU box, hence committed fixtures).  Run:  python tests/golden/make_golden.py
+
+Fixtures (all fp32, fixed seeds):
+  p2p_same.pt      AttentionReplace(prompts identical), shipped config of inference_lora.py:156 -> alpha table, mapper,
+                   probabilities in/out for self & cross layers at steps inside/outside the self-replace window.
+  p2p_edit.pt      AttentionReplace with a one-word edit and a partial cross_replace window (toy tokenizer).
+  ip_attn.pt       IPAttnProcessor / IPAttnProcessor2_0 / AttnProcessor under a shim Attention module.
+  resampler.pt     Resampler(dim=128, depth=2, heads=4, 16 queries, 512 -> 256).
+"""
+import os
+import sys
+
+import torch
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REF)
+
+
+class ToyTokenizer:
+    """Whitespace tokenizer with BOS/EOS, enough for seq_aligner/p2p_utils (encode/decode)."""
+
+    def __init__(self):
+        self.vocab = {}
+        self.inv = {}
+
+    def encode(self, text):
+        ids = [0]
+        for w in text.split(" "):
+            if w not in self.vocab:
+                self.vocab[w] = len(self.vocab) + 2
+                self.inv[self.vocab[w]] = w
+            ids.append(self.vocab[w])
+        return ids + [1]
+
+    def decode(self, ids):
+        return " ".join(self.inv.get(i, "") for i in ids)
+
+
+def run_controller(ctrl, layers, steps, batch_heads, seed):
+    """Drive the controller like the 140-layer UNet would: list of (is_cross, N, L)."""
+    g = torch.Generator().manual_seed(seed)
+    rec = []
+    ctrl.num_att_layers = len(layers)
+    for s in range(steps):
+        for (is_cross, n, l) in layers:
+            p = torch.softmax(torch.randn(batch_heads, n, l, generator=g), dim=-1)
+            inp = p.clone()
+            out = ctrl(p, is_cross, "mid")
+            rec.append({"step": s, "is_cross": is_cross, "in": inp, "out": out.clone(), "cur_step": ctrl.cur_step,
+                        "cur_att_layer": ctrl.cur_att_layer})
+    return rec
+
+
+def make_p2p():
+    from src.prompt_attention.p2p_attention import AttentionReplace
+    tok = ToyTokenizer()
+    prompt = "a photo of a man and a woman on the beach"
+    layers = [(False, 16, 16), (True, 16, 77), (False, 64, 64), (True, 64, 77)]
+    # shipped configuration: inference_lora.py:156 (num_steps=50, cross 1.0, self 0.4), threshold width*height
+    ctrl = AttentionReplace([prompt] * 2, 50, cross_replace_steps={"default_": 1.}, self_replace_steps=0.4,
+                            tokenizer=tok, device="cpu", dtype=torch.float32, width=4, height=4)
+    rec = run_controller(ctrl, layers, 22, 4 * 2, seed=0)  # batch 4 (CFG x 2 images) x 2 heads
+    keep = [r for r in rec if r["step"] in (0, 19, 20, 21)]
+    torch.save({"prompts": [prompt] * 2, "alpha": ctrl.cross_replace_alpha.clone(), "mapper": ctrl.mapper.clone(),
+                "num_self_replace": ctrl.num_self_replace, "layers": layers, "records": keep, "width": 4, "height": 4,
+                "heads": 2}, os.path.join(OUT, "p2p_same.pt"))
+    p2 = "a photo of a dog and a woman on the beach"
+    ctrl = AttentionReplace([prompt, p2], 10, cross_replace_steps={"default_": 0.6, "dog": (0.2, 0.9)},
+                            self_replace_steps=0.3, tokenizer=tok, device="cpu", dtype=torch.float32, width=4, height=4)
+    rec = run_controller(ctrl, layers, 10, 4 * 2, seed=1)
+    torch.save({"prompts": [prompt, p2], "alpha": ctrl.cross_replace_alpha.clone(), "mapper": ctrl.mapper.clone(),
+                "num_self_replace": ctrl.num_self_replace, "layers": layers, "records": rec, "width": 4, "height": 4,
+                "heads": 2, "num_steps": 10, "cross": {"default_": 0.6, "dog": (0.2, 0.9)}, "self": 0.3},
+               os.path.join(OUT, "p2p_edit.pt"))
+
+
+class ShimAttention(torch.nn.Module):
+    """Minimal stand-in for diffusers Attention with the attributes the reference processors read
+    (src/pipelines/lora_pipeline.py:81-131)."""
+
+    def __init__(self, dim, ctx_dim, heads):
+        super().__init__()
+        self.heads = heads
+        self.scale = (dim // heads) ** -0.5
+        self.to_q = torch.nn.Linear(dim, dim, bias=False)
+        self.to_k = torch.nn.Linear(ctx_dim, dim, bias=False)
+        self.to_v = torch.nn.Linear(ctx_dim, dim, bias=False)
+        self.to_out = torch.nn.ModuleList([torch.nn.Linear(dim, dim), torch.nn.Dropout(0.0)])
+        self.spatial_norm = None
+        self.group_norm = None
+        self.norm_cross = False
+        self.residual_connection = False
+        self.rescale_output_factor = 1.0
+
+    def prepare_attention_mask(self, m, *a, **k):
+        return m
+
+    def head_to_batch_dim(self, t):
+        b, n, c = t.shape
+        return t.reshape(b, n, self.heads, c // self.heads).permute(0, 2, 1, 3).reshape(b * self.heads, n, -1)
+
+    def batch_to_head_dim(self, t):
+        bh, n, d = t.shape
+        return t.reshape(bh // self.heads, self.heads, n, d).permute(0, 2, 1, 3).reshape(bh // self.heads, n, -1)
+
+    def get_attention_scores(self, q, k, mask=None):
+        s = torch.baddbmm(torch.empty(q.shape[0], q.shape[1], k.shape[1]), q, k.transpose(-1, -2), beta=0,
+                          alpha=self.scale)
+        return s.softmax(dim=-1)
+
+
+def make_ip():
+    from src.ip_adapter.attention_processor import AttnProcessor, IPAttnProcessor, IPAttnProcessor2_0
+    torch.manual_seed(0)
+    dim, ctx_dim, heads = 128, 96, 2
+    attn = ShimAttention(dim, ctx_dim, heads)
+    ip = IPAttnProcessor(dim, ctx_dim, scale=0.8, num_tokens=16)
+    ip2 = IPAttnProcessor2_0(dim, ctx_dim, scale=0.8, num_tokens=16)
+    ip2.load_state_dict(ip.state_dict())
+    x = torch.randn(2, 64, dim)
+    ctx = torch.randn(2, 77 + 16, ctx_dim)
+    with torch.no_grad():
+        y1 = ip(attn, x, ctx)
+        y2 = ip2(attn, x, ctx)
+        y_self = AttnProcessor()(attn2 := ShimAttention(dim, dim, heads), x)
+    torch.save({"attn": attn.state_dict(), "attn_self": attn2.state_dict(), "ip": ip.state_dict(), "x": x, "ctx": ctx,
+                "y_ip": y1, "y_ip2": y2, "y_self": y_self, "dim": dim, "ctx_dim": ctx_dim, "heads": heads,
+                "scale": 0.8, "num_tokens": 16}, os.path.join(OUT, "ip_attn.pt"))
+
+
+def make_resampler():
+    from src.ip_adapter.resampler import Resampler
+    torch.manual_seed(0)
+    r = Resampler(dim=128, depth=2, dim_head=32, heads=4, num_queries=16, embedding_dim=512, output_dim=256, ff_mult=4)
+    x = torch.randn(2, 1, 512)
+    with torch.no_grad():
+        y = r(x)
+    torch.save({"sd": r.state_dict(), "x": x, "y": y, "heads": 4, "dim_head": 32}, os.path.join(OUT, "resampler.pt"))
+
+
+if __name__ == "__main__":
+    make_p2p()
+    make_ip()
+    make_resampler()
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".pt"):
+            print(f, os.path.getsize(os.path.join(OUT, f)))
