@@ -34,6 +34,7 @@ typedef struct {
  * pixels read as zero = conv padding), channels [a_c0, a_c0+k_len); weight columns [b_k0, b_k0+k_len). */
 typedef struct {
     int32_t a_idx, dx, dy, a_c0, k_len, b_k0;
+    int32_t b_idx; /* 0: columns of w, 1: columns of w2 (e.g. the LoRA up-projection B, kept un-merged) */
 } omg_seg;
 
 enum { OMG_EPI_NONE = 0, OMG_EPI_GEGLU = 1, OMG_EPI_SILU = 2 };
@@ -54,6 +55,8 @@ typedef struct {
     int32_t n_segs;
     const void* w;      /* [N, Ktot] row-major fp16 */
     int32_t N, Ktot;
+    const void* w2;     /* optional second weight matrix [N, K2tot] (segments with b_idx == 1) or NULL */
+    int32_t K2tot;
     omg_view4 d;        /* output view; d.W/H/B define the pixel grid the tiles walk */
     const void* bias;   /* [N] fp16 or NULL */
     const void* rowvec; /* [B, rowvec_ld] fp16 or NULL: per-image additive vector (time-embedding projection) */
@@ -142,6 +145,10 @@ int omg_fuse_step(const omg_fuse_desc* desc, void* stream);
  * terms over projected V.
  */
 int omg_ctx_mix(const void* ctx, const void* coef, void* out, int B, int L, int C, void* stream);
+
+/* y = a + alpha * b over n fp16 elements (n % 8 == 0): ControlNet residual injection
+ * (down_block_additional_residuals / mid_block_additional_residual, src/pipelines/lora_pipeline.py:546-556). */
+int omg_axpy(const void* a, const void* b, float alpha, void* y, long long n, void* stream);
 
 /* Error string of the last failing call on this thread (never NULL). */
 const char* omg_last_error(void);

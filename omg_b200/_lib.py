@@ -20,12 +20,13 @@ class View4(C.Structure):
 
 class Seg(C.Structure):
     _fields_ = [("a_idx", C.c_int32), ("dx", C.c_int32), ("dy", C.c_int32), ("a_c0", C.c_int32),
-                ("k_len", C.c_int32), ("b_k0", C.c_int32)]
+                ("k_len", C.c_int32), ("b_k0", C.c_int32), ("b_idx", C.c_int32)]
 
 
 class GemmDesc(C.Structure):
     _fields_ = [("a", View4 * OMG_MAX_A), ("n_a", C.c_int32), ("segs", Seg * OMG_MAX_SEGS), ("n_segs", C.c_int32),
-                ("w", C.c_void_p), ("N", C.c_int32), ("Ktot", C.c_int32), ("d", View4), ("bias", C.c_void_p),
+                ("w", C.c_void_p), ("N", C.c_int32), ("Ktot", C.c_int32), ("w2", C.c_void_p), ("K2tot", C.c_int32),
+                ("d", View4), ("bias", C.c_void_p),
                 ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int32), ("residual", C.c_void_p),
                 ("residual_ld", C.c_int32), ("epilogue", C.c_int32), ("block_n", C.c_int32)]
 
@@ -60,6 +61,7 @@ SYMBOLS = {
                                 C.c_void_p]),
     "omg_fuse_step": (C.c_int, [C.POINTER(FuseDesc), C.c_void_p]),
     "omg_ctx_mix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "omg_axpy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p]),
     "omg_last_error": (C.c_char_p, []),
     "omg_version": (C.c_char_p, []),
     "omg_launch_count": (C.c_uint64, []),

@@ -126,9 +126,36 @@ __global__ void ctx_mix_kernel(const __half* __restrict__ ctx, const float* __re
     out[((size_t)b * L + w) * C + c] = __float2half_rn(acc);
 }
 
+__global__ void axpy_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, float alpha,
+                            uint4* __restrict__ y, long long nvec) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    const uint4 ua = a[i], ub = b[i];
+    const __half2* ha = reinterpret_cast<const __half2*>(&ua);
+    const __half2* hb = reinterpret_cast<const __half2*>(&ub);
+    uint4 o;
+    __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const float2 fa = __half22float2(ha[t]), fb = __half22float2(hb[t]);
+        ho[t] = __floats2half2_rn(fa.x + alpha * fb.x, fa.y + alpha * fb.y);
+    }
+    y[i] = o;
+}
+
 }  // namespace omg
 
 using namespace omg;
+
+extern "C" int omg_axpy(const void* a, const void* b, float alpha, void* y, long long n, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    OMG_CHECK(a && b && y && n > 0 && n % 8 == 0, "omg_axpy: bad arguments");
+    const long long nvec = n / 8;
+    axpy_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, stream>>>(static_cast<const uint4*>(a),
+                                                                     static_cast<const uint4*>(b), alpha,
+                                                                     static_cast<uint4*>(y), nvec);
+    return check_launch("axpy_kernel");
+}
 
 extern "C" int omg_fuse_step(const omg_fuse_desc* d, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

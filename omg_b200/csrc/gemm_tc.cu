@@ -30,12 +30,12 @@ constexpr int GEMM_THREADS = 192;
 constexpr int STAGING_BYTES = 4 * 2 * 2048;  // 4 epilogue warps x double buffer x (32 rows x 64 B)
 
 struct SegDev {
-    int a_map, dx, dy, a_c0, k_blocks, b_k0;
+    int a_map, dx, dy, a_c0, k_blocks, b_k0, b_map;
 };
 
 struct alignas(64) GemmParams {
     CUtensorMap a_maps[OMG_MAX_A];
-    CUtensorMap b_map;
+    CUtensorMap b_maps[2];
     CUtensorMap d_map;
     SegDev segs[OMG_MAX_SEGS];
     int n_segs;
@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < OMG_MAX_A; ++i) tma_prefetch_desc(&p.a_maps[i]);
-        tma_prefetch_desc(&p.b_map);
+        tma_prefetch_desc(&p.b_maps[0]);
+        tma_prefetch_desc(&p.b_maps[1]);
         tma_prefetch_desc(&p.d_map);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                         tma_load_4d(a_dst, &p.a_maps[sg.a_map], &full_bar[stage], sg.a_c0 + kb * BK, w0 + sg.dx,
                                     h0 + sg.dy, b);
-                        tma_load_2d(b_dst, &p.b_map, &full_bar[stage], sg.b_k0 + kb * BK, n0);
+                        tma_load_2d(b_dst, &p.b_maps[sg.b_map], &full_bar[stage], sg.b_k0 + kb * BK, n0);
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -424,7 +425,15 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
         const uint64_t dims[2] = {(uint64_t)d->Ktot, (uint64_t)d->N};
         const uint64_t strides[2] = {1, (uint64_t)d->Ktot};
         const uint32_t box[2] = {BK, (uint32_t)bn};
-        if (make_tmap_f16(&p.b_map, d->w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+        if (make_tmap_f16(&p.b_maps[0], d->w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+        p.b_maps[1] = p.b_maps[0];
+    }
+    if (d->w2 != nullptr) {
+        OMG_CHECK(d->K2tot >= 8 && d->K2tot % 8 == 0, "omg_gemm: K2tot=%d must be a positive multiple of 8", d->K2tot);
+        const uint64_t dims[2] = {(uint64_t)d->K2tot, (uint64_t)d->N};
+        const uint64_t strides[2] = {1, (uint64_t)d->K2tot};
+        const uint32_t box[2] = {BK, (uint32_t)bn};
+        if (make_tmap_f16(&p.b_maps[1], d->w2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     }
     if (view_to_tmap(&p.d_map, d->d, 32, p.store_w, p.store_h, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
 
@@ -434,13 +443,15 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
         OMG_CHECK(sg.a_idx >= 0 && sg.a_idx < d->n_a, "omg_gemm: segment %d references A view %d", s, sg.a_idx);
         OMG_CHECK(sg.k_len > 0 && sg.a_c0 >= 0 && sg.b_k0 >= 0 && sg.a_c0 + sg.k_len <= d->a[sg.a_idx].C,
                   "omg_gemm: segment %d has a bad K range", s);
-        OMG_CHECK(sg.b_k0 + sg.k_len <= d->Ktot, "omg_gemm: segment %d exceeds weight K (%d + %d > %d)", s, sg.b_k0,
-                  sg.k_len, d->Ktot);
+        OMG_CHECK(sg.b_idx == 0 || (sg.b_idx == 1 && d->w2 != nullptr), "omg_gemm: segment %d has a bad b_idx", s);
+        const int ktot_s = sg.b_idx ? d->K2tot : d->Ktot;
+        OMG_CHECK(sg.b_k0 + sg.k_len <= ktot_s, "omg_gemm: segment %d exceeds weight K (%d + %d > %d)", s, sg.b_k0,
+                  sg.k_len, ktot_s);
         // A K-tail (k_len % 64 != 0) is only legal when the over-read of A is zero-filled, i.e. the segment ends
         // at the end of the A view's channel range.
         OMG_CHECK(sg.k_len % BK == 0 || sg.a_c0 + sg.k_len == d->a[sg.a_idx].C,
                   "omg_gemm: segment %d: K tail must end at the A view's last channel", s);
-        p.segs[s] = SegDev{sg.a_idx, sg.dx, sg.dy, sg.a_c0, (sg.k_len + BK - 1) / BK, sg.b_k0};
+        p.segs[s] = SegDev{sg.a_idx, sg.dx, sg.dy, sg.a_c0, (sg.k_len + BK - 1) / BK, sg.b_k0, sg.b_idx};
     }
 
     if (geglu) return launch_gemm<256, OMG_EPI_GEGLU>(p, stream);

@@ -35,16 +35,18 @@ def _ptr(t):
 
 
 def gemm(a_views, segs, w, N, Ktot, d_view, bias=None, rowvec=None, rowvec_ld=0, residual=None, residual_ld=0,
-         epilogue=L.EPI_NONE, block_n=0):
+         epilogue=L.EPI_NONE, block_n=0, w2=None):
     d = L.GemmDesc()
     d.n_a = len(a_views)
     for i, v in enumerate(a_views):
         d.a[i] = v
     d.n_segs = len(segs)
     for i, s in enumerate(segs):
-        d.segs[i] = L.Seg(*s)
+        d.segs[i] = L.Seg(*s) if len(s) == 7 else L.Seg(*s, 0)
     d.w = w.data_ptr()
     d.N, d.Ktot = N, Ktot
+    if w2 is not None:
+        d.w2, d.K2tot = w2.data_ptr(), w2.shape[1]
     d.d = d_view
     d.bias = _ptr(bias)
     d.rowvec = _ptr(rowvec)
@@ -56,10 +58,11 @@ def gemm(a_views, segs, w, N, Ktot, d_view, bias=None, rowvec=None, rowvec_ld=0,
     L.check(L.load().omg_gemm(C.byref(d), _stream()), "omg_gemm")
 
 
-def linear(x, w, bias=None, residual=None, out=None, epilogue=L.EPI_NONE, extra=None, block_n=0):
-    """out[M, N'] = epi(x[M,K] @ w[N, :K]^T (+ sum_i extra_i.x[M,Ki] @ w[N, off_i:off_i+Ki]^T) + bias) + residual.
+def linear(x, w, bias=None, residual=None, out=None, epilogue=L.EPI_NONE, extra=None, block_n=0, lora=None):
+    """out[M, N'] = epi(x[M,K] @ w[N, :K]^T (+ extra K-segments) + bias) + residual.
 
-    `extra` = list of (tensor [M,Ki], weight column offset): further K-segments (LoRA deltas  s*B(Ax)).
+    `extra` = list of (tensor [M,Ki], column offset into w): further K-segments of the same weight matrix.
+    `lora`  = (t [M,R], w2 [N,R]): un-merged LoRA delta  t @ w2^T  with t = A x (scales folded into w2).
     """
     _chk16(x)
     M, K = x.shape
@@ -72,8 +75,13 @@ def linear(x, w, bias=None, residual=None, out=None, epilogue=L.EPI_NONE, extra=
     for t, off in (extra or []):
         views.append(view4(t))
         segs.append((len(views) - 1, 0, 0, 0, t.shape[1], off))
+    w2 = None
+    if lora is not None:
+        t, w2 = lora
+        views.append(view4(t))
+        segs.append((len(views) - 1, 0, 0, 0, t.shape[1], 0, 1))
     gemm(views, segs, w, N, Ktot, view4(out), bias=bias, residual=residual,
-         residual_ld=0 if residual is None else residual.stride(0), epilogue=epilogue, block_n=block_n)
+         residual_ld=0 if residual is None else residual.stride(0), epilogue=epilogue, block_n=block_n, w2=w2)
     return out
 
 
@@ -201,6 +209,16 @@ def fuse_step(noise_main, noise_concepts, masks, guidance, sigma, sigma_next, la
     d.latents_f16 = _ptr(latents_f16)
     d.HW = latents.shape[1] * latents.shape[2] if latents.dim() == 4 else latents.shape[1]
     L.check(L.load().omg_fuse_step(C.byref(d), _stream()), "omg_fuse_step")
+
+
+def axpy(a, b, alpha=1.0, out=None):
+    """out = a + alpha * b (fp16, same shape)."""
+    _chk16(a)
+    if out is None:
+        out = torch.empty_like(a)
+    L.check(L.load().omg_axpy(a.data_ptr(), b.data_ptr(), float(alpha), out.data_ptr(), a.numel(), _stream()),
+            "omg_axpy")
+    return out
 
 
 def ctx_mix(ctx, coef, out=None):

@@ -19,7 +19,7 @@ class EulerDiscrete:
     def set_timesteps(self, n: int):
         step_ratio = self.num_train_timesteps // n
         ts = (np.arange(0, n) * step_ratio).round()[::-1].copy().astype(np.float32) + self.steps_offset
-        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
         sig = np.interp(ts, np.arange(0, len(sig)), sig)
         self.sigmas = torch.from_numpy(np.concatenate([sig, [0.0]]).astype(np.float32))
         self.timesteps = torch.from_numpy(ts)

@@ -57,22 +57,22 @@ def make_p2p():
     from src.prompt_attention.p2p_attention import AttentionReplace
     tok = ToyTokenizer()
     prompt = "a photo of a man and a woman on the beach"
-    layers = [(False, 16, 16), (True, 16, 77), (False, 64, 64), (True, 64, 77)]
+    layers = [(False, 16, 16), (True, 16, 77), (False, 32, 32), (True, 32, 77)]
     # shipped configuration: inference_lora.py:156 (num_steps=50, cross 1.0, self 0.4), threshold width*height
     ctrl = AttentionReplace([prompt] * 2, 50, cross_replace_steps={"default_": 1.}, self_replace_steps=0.4,
                             tokenizer=tok, device="cpu", dtype=torch.float32, width=4, height=4)
-    rec = run_controller(ctrl, layers, 22, 4 * 2, seed=0)  # batch 4 (CFG x 2 images) x 2 heads
+    rec = run_controller(ctrl, layers, 22, 4, seed=0)  # batch 4 (CFG x 2 images) x 1 head
     keep = [r for r in rec if r["step"] in (0, 19, 20, 21)]
     torch.save({"prompts": [prompt] * 2, "alpha": ctrl.cross_replace_alpha.clone(), "mapper": ctrl.mapper.clone(),
                 "num_self_replace": ctrl.num_self_replace, "layers": layers, "records": keep, "width": 4, "height": 4,
-                "heads": 2}, os.path.join(OUT, "p2p_same.pt"))
+                "heads": 1}, os.path.join(OUT, "p2p_same.pt"))
     p2 = "a photo of a dog and a woman on the beach"
     ctrl = AttentionReplace([prompt, p2], 10, cross_replace_steps={"default_": 0.6, "dog": (0.2, 0.9)},
                             self_replace_steps=0.3, tokenizer=tok, device="cpu", dtype=torch.float32, width=4, height=4)
-    rec = run_controller(ctrl, layers, 10, 4 * 2, seed=1)
+    rec = run_controller(ctrl, layers, 10, 4, seed=1)
     torch.save({"prompts": [prompt, p2], "alpha": ctrl.cross_replace_alpha.clone(), "mapper": ctrl.mapper.clone(),
                 "num_self_replace": ctrl.num_self_replace, "layers": layers, "records": rec, "width": 4, "height": 4,
-                "heads": 2, "num_steps": 10, "cross": {"default_": 0.6, "dog": (0.2, 0.9)}, "self": 0.3},
+                "heads": 1, "num_steps": 10, "cross": {"default_": 0.6, "dog": (0.2, 0.9)}, "self": 0.3},
                os.path.join(OUT, "p2p_edit.pt"))
 
 

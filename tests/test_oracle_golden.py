@@ -1,0 +1,117 @@
+"""CPU: the oracle restatements against golden vectors produced by the UNMODIFIED reference modules
+(tests/golden/make_golden.py; the reference tree does not travel to the GPU box)."""
+import math
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+from make_golden import ToyTokenizer  # noqa: E402  (pure helper; does not import the reference)
+
+from oracle import p2p, unet  # noqa: E402
+from oracle.resampler import resampler_forward  # noqa: E402
+from oracle.scheduler import EulerDiscrete  # noqa: E402
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _replay(ctrl, layers, steps, bh, seed):
+    g = torch.Generator().manual_seed(seed)
+    ctrl.num_att_layers = len(layers)
+    rec = []
+    for s in range(steps):
+        for (is_cross, n, l) in layers:
+            p = torch.softmax(torch.randn(bh, n, l, generator=g), dim=-1)
+            out = ctrl(p.clone(), is_cross, "mid")
+            rec.append((s, is_cross, p, out, ctrl.cur_step, ctrl.cur_att_layer))
+    return rec
+
+
+def test_p2p_shipped_config_matches_reference():
+    d = torch.load(os.path.join(G, "p2p_same.pt"))
+    ctrl = p2p.AttentionReplaceOracle(d["prompts"], 50, {"default_": 1.0}, 0.4, d["width"], d["height"],
+                                      tokenizer=ToyTokenizer())
+    assert torch.equal(ctrl.cross_replace_alpha, d["alpha"])
+    assert torch.equal(ctrl.mapper, d["mapper"])
+    assert tuple(ctrl.num_self_replace) == tuple(d["num_self_replace"]) == (0, 20)
+    assert torch.equal(ctrl.mapper[0], torch.eye(77))
+    assert ctrl.cross_replace_alpha.unique().tolist() == [1.0]
+    rec = _replay(ctrl, d["layers"], 22, 4, seed=0)
+    by_key = {(s, i % len(d["layers"])): r for i, r in enumerate(rec) for s in [r[0]]}
+    n = 0
+    for j, r in enumerate(d["records"]):
+        li = j % len(d["layers"])
+        mine = by_key[(r["step"], li)]
+        assert torch.equal(mine[2], r["in"])
+        assert torch.allclose(mine[3], r["out"], atol=1e-7)
+        assert mine[4] == r["cur_step"] and mine[5] == r["cur_att_layer"]
+        n += 1
+    assert n == 16
+
+
+def test_p2p_word_edit_matches_reference():
+    d = torch.load(os.path.join(G, "p2p_edit.pt"))
+    ctrl = p2p.AttentionReplaceOracle(d["prompts"], d["num_steps"], dict(d["cross"]), d["self"], d["width"],
+                                      d["height"], tokenizer=ToyTokenizer())
+    assert torch.equal(ctrl.cross_replace_alpha, d["alpha"])
+    assert torch.equal(ctrl.mapper, d["mapper"])
+    rec = _replay(ctrl, d["layers"], 10, 4, seed=1)
+    assert len(rec) == len(d["records"])
+    for mine, r in zip(rec, d["records"]):
+        assert torch.equal(mine[2], r["in"])
+        assert torch.allclose(mine[3], r["out"], atol=1e-6)
+        assert mine[4] == r["cur_step"]
+
+
+def test_p2p_length_mismatch_raises():
+    with pytest.raises(ValueError):
+        p2p.replacement_mapper(["a b c", "a b"], ToyTokenizer())
+
+
+def test_ip_attention_matches_reference():
+    d = torch.load(os.path.join(G, "ip_attn.pt"))
+    cfg = unet.UNetConfig(head_dim=d["dim"] // d["heads"])
+    sd = {"a." + k: v for k, v in d["attn"].items()}
+    c = unet.Ctx(sd, cfg, ip_weights={"a": (d["ip"]["to_k_ip.weight"], d["ip"]["to_v_ip.weight"])},
+                 ip_tokens=d["num_tokens"], ip_scale=d["scale"])
+    y = unet.attention(c, "a", d["x"], d["ctx"])
+    assert torch.allclose(y, d["y_ip"], atol=2e-6)
+    assert torch.allclose(y, d["y_ip2"], atol=2e-6)
+    c2 = unet.Ctx({"a." + k: v for k, v in d["attn_self"].items()}, cfg)
+    assert torch.allclose(unet.attention(c2, "a", d["x"]), d["y_self"], atol=2e-6)
+
+
+def test_resampler_matches_reference():
+    d = torch.load(os.path.join(G, "resampler.pt"))
+    y = resampler_forward(d["sd"], d["x"], d["heads"], d["dim_head"])
+    assert torch.allclose(y, d["y"], atol=2e-6)
+
+
+def test_sdxl_topology_counts():
+    cfg = unet.UNetConfig.sdxl()
+    n = sum(math.prod(s) for s in unet.param_shapes(cfg).values())
+    assert n == 2_567_463_684                                   # SDXL-base UNet parameter count
+    nc = sum(math.prod(s) for s in unet.param_shapes(cfg, controlnet=True).values())
+    assert nc == 1_251_014_160                                  # SDXL ControlNet
+    names = unet.attention_names(cfg)
+    assert len(names) == 140 and sum(n_.endswith("attn2") for n_ in names) == 70
+    assert abs(unet.unet_flops(cfg, 128, 128) / 1e12 - 6.761) < 2e-3
+    assert abs(unet.unet_flops(cfg, 64, 64) / 1e12 - 1.589) < 2e-3
+
+
+def test_euler_schedule_known_values():
+    s = EulerDiscrete()
+    sig_all = ((1 - s.alphas_cumprod) / s.alphas_cumprod) ** 0.5
+    assert abs(float(sig_all[-1]) - 14.6146) < 1e-3             # the published SD/SDXL sigma_max
+    ts = s.set_timesteps(30)
+    assert ts[0].item() == 958.0 and ts[-1].item() == 1.0 and len(ts) == 30   # leading spacing, offset 1
+    assert s.sigmas[-1].item() == 0.0 and len(s.sigmas) == 31
+    assert abs(s.init_noise_sigma - math.sqrt(float(s.sigmas[0]) ** 2 + 1)) < 1e-6
+    ts50 = s.set_timesteps(50)
+    assert ts50[0].item() == 981.0
+    x = torch.randn(2, 4, 8, 8)
+    eps = torch.randn(2, 4, 8, 8)
+    y = s.step(eps, 3, x)
+    assert torch.allclose(y, x + eps * (s.sigmas[4] - s.sigmas[3]), atol=1e-5)
