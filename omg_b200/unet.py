@@ -1,0 +1,480 @@
+"""SDXL UNet / ControlNet executor over the C-ABI kernels.
+
+Replaces `self.unet(...)`, `concept_models.unet(...)` and `self.controlnet(...)` of the reference loops
+(src/pipelines/lora_pipeline.py:520-529,546-566,592-599; src/pipelines/instantid_pipeline.py:580-616,639-674).
+
+Layout: activations channels-last fp16, (B,H,W,C) == (B*H*W tokens, C); latents enter/leave as (B,H,W,8) with
+channels 4..7 zero.  Per UNet call the launch sequence is static, so it is captured once per variant in a CUDA graph
+and replayed (no host work, no syncs inside a step).
+
+What is hoisted out of the per-step path (all step-invariant in the reference too):
+  * time / added-cond embeddings and every ResBlock's time_emb_proj: one GEMM table for all timesteps per call;
+  * cross-attention K/V of the text (and IP-adapter image) tokens: once per call per context / LoRA set;
+  * the ControlNet conditioning embedding of the (constant) condition image: once per call.
+"""
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .config import UNetConfig, resnet_names, transformer_names
+
+
+def _f16(t, dev):
+    return t.to(device=dev, dtype=torch.float16).contiguous()
+
+
+def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
+    """diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos | sin], fp32."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+    ang = t.float()[:, None] * freqs[None, :]
+    return torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1)
+
+
+class PackedUNet:
+    """Weights of one UNet (or ControlNet trunk) repacked for the kernels, resident in HBM as fp16."""
+
+    def __init__(self, cfg: UNetConfig, state_dict: Dict[str, torch.Tensor], device="cuda", controlnet: bool = False):
+        self.cfg, self.device, self.controlnet = cfg, torch.device(device), controlnet
+        sd = state_dict
+        dev = self.device
+        self.p: Dict[str, torch.Tensor] = {}
+        P = self.p
+
+        def conv_w(name, pad_in=0, pad_out=0):
+            w = sd[name + ".weight"].to(dev, torch.float16)
+            b = sd[name + ".bias"].to(dev, torch.float16)
+            if pad_in:
+                w = torch.cat([w, w.new_zeros(w.shape[0], pad_in, *w.shape[2:])], dim=1)
+            if pad_out:
+                w = torch.cat([w, w.new_zeros(pad_out, *w.shape[1:])], dim=0)
+                b = torch.cat([b, b.new_zeros(pad_out)])
+            if w.shape[2] == 3:
+                w = ops.pack_conv3x3_weight(w)
+            else:
+                w = w.reshape(w.shape[0], w.shape[1]).contiguous()
+            return w, b.contiguous()
+
+        boc = cfg.block_out_channels
+        P["conv_in.w"], P["conv_in.b"] = conv_w("conv_in", pad_in=8 - cfg.in_channels)
+        for n in ("time_embedding.linear_1", "time_embedding.linear_2", "add_embedding.linear_1",
+                  "add_embedding.linear_2"):
+            P[n + ".w"], P[n + ".b"] = _f16(sd[n + ".weight"], dev), _f16(sd[n + ".bias"], dev)
+        # every ResBlock's time_emb_proj concatenated: one GEMM produces all of them for all timesteps
+        self.res_names = resnet_names(cfg, controlnet)
+        self.temb_off: Dict[str, int] = {}
+        tw, tb, off = [], [], 0
+        for name, cout in self.res_names:
+            self.temb_off[name] = off
+            tw.append(sd[name + ".time_emb_proj.weight"])
+            tb.append(sd[name + ".time_emb_proj.bias"])
+            off += cout
+        self.temb_cols = off
+        P["temb_all.w"] = _f16(torch.cat(tw, dim=0), dev)
+        P["temb_all.b"] = _f16(torch.cat(tb, dim=0), dev)
+        for name, cout in self.res_names:
+            cin = sd[name + ".conv1.weight"].shape[1]
+            P[name + ".g1"], P[name + ".b1"] = _f16(sd[name + ".norm1.weight"], dev), _f16(sd[name + ".norm1.bias"], dev)
+            P[name + ".g2"], P[name + ".b2"] = _f16(sd[name + ".norm2.weight"], dev), _f16(sd[name + ".norm2.bias"], dev)
+            P[name + ".w1"], P[name + ".bias1"] = conv_w(name + ".conv1")
+            w2, b2 = conv_w(name + ".conv2")
+            if (name + ".conv_shortcut.weight") in sd:
+                ws, bs = conv_w(name + ".conv_shortcut")
+                w2 = torch.cat([w2, ws], dim=1).contiguous()
+                b2 = (b2.float() + bs.float()).half()
+            P[name + ".w2"], P[name + ".bias2"] = w2, b2
+        self.tr_names = transformer_names(cfg, controlnet)
+        for name, ch, layers in self.tr_names:
+            P[name + ".norm.g"], P[name + ".norm.b"] = _f16(sd[name + ".norm.weight"], dev), _f16(sd[name + ".norm.bias"], dev)
+            for lin in ("proj_in", "proj_out"):
+                P[f"{name}.{lin}.w"], P[f"{name}.{lin}.b"] = _f16(sd[f"{name}.{lin}.weight"], dev), _f16(sd[f"{name}.{lin}.bias"], dev)
+            for k in range(layers):
+                b = f"{name}.transformer_blocks.{k}"
+                for m in ("norm1", "norm2", "norm3"):
+                    P[f"{b}.{m}.g"], P[f"{b}.{m}.b"] = _f16(sd[f"{b}.{m}.weight"], dev), _f16(sd[f"{b}.{m}.bias"], dev)
+                P[f"{b}.attn1.qkv.w"] = _f16(torch.cat([sd[f"{b}.attn1.to_q.weight"], sd[f"{b}.attn1.to_k.weight"],
+                                                        sd[f"{b}.attn1.to_v.weight"]], dim=0), dev)
+                P[f"{b}.attn2.q.w"] = _f16(sd[f"{b}.attn2.to_q.weight"], dev)
+                P[f"{b}.attn2.kv.w"] = _f16(torch.cat([sd[f"{b}.attn2.to_k.weight"], sd[f"{b}.attn2.to_v.weight"]],
+                                                      dim=0), dev)
+                for a in ("attn1", "attn2"):
+                    P[f"{b}.{a}.out.w"], P[f"{b}.{a}.out.b"] = _f16(sd[f"{b}.{a}.to_out.0.weight"], dev), _f16(sd[f"{b}.{a}.to_out.0.bias"], dev)
+                wi, bi = ops.pack_geglu_weight(sd[f"{b}.ff.net.0.proj.weight"], sd[f"{b}.ff.net.0.proj.bias"])
+                P[f"{b}.ff1.w"], P[f"{b}.ff1.b"] = _f16(wi, dev), _f16(bi, dev)
+                P[f"{b}.ff2.w"], P[f"{b}.ff2.b"] = _f16(sd[f"{b}.ff.net.2.weight"], dev), _f16(sd[f"{b}.ff.net.2.bias"], dev)
+        nb = len(boc)
+        for i in range(nb - 1):
+            P[f"down{i}.w"], P[f"down{i}.b"] = conv_w(f"down_blocks.{i}.downsamplers.0.conv")
+        if controlnet:
+            cec = cfg.cond_embed_channels
+            P["cond.conv_in.w"], P["cond.conv_in.b"] = conv_w("controlnet_cond_embedding.conv_in", pad_in=5)
+            for i in range(2 * (len(cec) - 1)):
+                P[f"cond.{i}.w"], P[f"cond.{i}.b"] = conv_w(f"controlnet_cond_embedding.blocks.{i}")
+            P["cond.conv_out.w"], P["cond.conv_out.b"] = conv_w("controlnet_cond_embedding.conv_out")
+            self.n_skips = 1 + nb * cfg.layers_per_block + (nb - 1)
+            for i in range(self.n_skips):
+                P[f"zero{i}.w"], P[f"zero{i}.b"] = conv_w(f"controlnet_down_blocks.{i}")
+            P["zero_mid.w"], P["zero_mid.b"] = conv_w("controlnet_mid_block")
+        else:
+            for i in range(nb - 1):
+                P[f"up{i}.w"], P[f"up{i}.b"] = conv_w(f"up_blocks.{i}.upsamplers.0.conv")
+            P["norm_out.g"], P["norm_out.b"] = _f16(sd["conv_norm_out.weight"], dev), _f16(sd["conv_norm_out.bias"], dev)
+            P["conv_out.w"], P["conv_out.b"] = conv_w("conv_out", pad_out=8 - cfg.out_channels)
+        # LoRA sets: key -> {linear key -> (A_cat [R, in], B2 [N, R])}; IP-adapter weights
+        self.lora_sets: Dict[str, Dict[str, Tuple[torch.Tensor, torch.Tensor]]] = {}
+        self.ip: Optional[Dict[str, torch.Tensor]] = None
+        self.ip_scale, self.ip_tokens = 1.0, 16
+
+    # ------------------------------------------------------------------------------------------- adapters
+    def add_lora_set(self, key: str, adapters, global_scale: float = 1.0):
+        """Register a set of simultaneously active adapters (peft `set_adapters(names, adapter_weights)` +
+        `cross_attention_kwargs={'scale': s}`; src/pipelines/lora_pipeline.py:588-596).
+
+        adapters: list of (lora, adapter_weight); lora maps the diffusers Linear path to (A [r,in], B [out,r],
+        alpha/r).  The delta stays un-merged: t = A_cat x is one skinny GEMM, s*B is a second weight matrix whose
+        columns become extra K-segments of the main GEMM."""
+        dev = self.device
+        packed: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+
+        def cat_adapters(name):
+            As, Bs = [], []
+            for lora, wgt in adapters:
+                if name in lora:
+                    A, Bm, s = lora[name]
+                    As.append(A.float())
+                    Bs.append(Bm.float() * (s * wgt * global_scale))
+            if not As:
+                return None
+            return torch.cat(As, dim=0), torch.cat(Bs, dim=1)
+
+        def put(key_out, parts, geglu=False):
+            """parts: list of (A_cat [R_i,in], B [N_i,R_i]) for row blocks of a fused weight."""
+            if all(p is None for p in parts["ab"]):
+                return
+            As, rows = [], []
+            r_off = 0
+            r_tot = sum(0 if ab is None else ab[0].shape[0] for ab in parts["ab"])
+            for ab, n_rows in zip(parts["ab"], parts["rows"]):
+                blk = torch.zeros(n_rows, r_tot)
+                if ab is not None:
+                    A, Bm = ab
+                    As.append(A)
+                    blk[:, r_off:r_off + A.shape[0]] = Bm
+                    r_off += A.shape[0]
+                rows.append(blk)
+            B2 = torch.cat(rows, dim=0)
+            if geglu:
+                B2, _ = ops.pack_geglu_weight(B2)
+            packed[key_out] = (_f16(torch.cat(As, dim=0), dev), _f16(B2, dev))
+
+        for name, ch, layers in self.tr_names:
+            for lin in ("proj_in", "proj_out"):
+                put(f"{name}.{lin}", {"ab": [cat_adapters(f"{name}.{lin}")], "rows": [ch]})
+            for k in range(layers):
+                b = f"{name}.transformer_blocks.{k}"
+                put(f"{b}.attn1.qkv", {"ab": [cat_adapters(f"{b}.attn1.to_{x}") for x in "qkv"], "rows": [ch] * 3})
+                put(f"{b}.attn2.q", {"ab": [cat_adapters(f"{b}.attn2.to_q")], "rows": [ch]})
+                put(f"{b}.attn2.kv", {"ab": [cat_adapters(f"{b}.attn2.to_{x}") for x in "kv"], "rows": [ch] * 2})
+                for a in ("attn1", "attn2"):
+                    put(f"{b}.{a}.out", {"ab": [cat_adapters(f"{b}.{a}.to_out.0")], "rows": [ch]})
+                put(f"{b}.ff1", {"ab": [cat_adapters(f"{b}.ff.net.0.proj")], "rows": [8 * ch]}, geglu=True)
+                put(f"{b}.ff2", {"ab": [cat_adapters(f"{b}.ff.net.2")], "rows": [ch]})
+        known = set()
+        for lora, _ in adapters:
+            known |= set(lora.keys())
+        from .config import lora_target_names
+        unsupported = known - {n for n, _, _ in lora_target_names(self.cfg)}
+        if unsupported:
+            raise ValueError(f"LoRA targets outside the transformer Linears are not supported: {sorted(unsupported)[:4]}…")
+        self.lora_sets[key] = packed
+
+    def set_ip_adapter(self, ip_weights: Dict[str, Tuple[torch.Tensor, torch.Tensor]], scale: float = 1.0,
+                       num_tokens: int = 16):
+        """IPAttnProcessor weights (src/ip_adapter/attention_processor.py:107-108): attn2 path -> (to_k_ip, to_v_ip)."""
+        self.ip = {k: _f16(torch.cat([wk, wv], dim=0), self.device) for k, (wk, wv) in ip_weights.items()}
+        self.ip_scale, self.ip_tokens = float(scale), int(num_tokens)
+
+    def set_ip_adapter_scale(self, scale: float):
+        self.ip_scale = float(scale)
+
+    def num_attention_layers(self) -> int:
+        return 2 * sum(layers for _, _, layers in self.tr_names)
+
+
+class UNetRunner:
+    """One (model, batch, latent size) execution context: preallocated activations, hoisted per-call tables,
+    CUDA graphs per variant."""
+
+    def __init__(self, model: PackedUNet, batch: int, H: int, W: int, lora_key: Optional[str] = None,
+                 use_graphs: bool = True):
+        self.m, self.B, self.H, self.W = model, batch, H, W
+        self.lora = model.lora_sets[lora_key] if lora_key else {}
+        self.dev = model.device
+        self.ws: Dict[str, torch.Tensor] = {}
+        self.use_graphs = use_graphs
+        self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.warm: set = set()
+        self.temb_table = None
+        self.kv: Dict[str, torch.Tensor] = {}
+        self.kv_ip: Dict[str, torch.Tensor] = {}
+        self.ctx_rows = batch
+        self.sample_in = self.buf("sample_in", (batch, H, W, 8))
+        self.sample_in.zero_()
+        self.temb_step = self.buf("temb_step", (batch, model.temb_cols))
+        self.cross_items: List[List[tuple]] = []
+        self.cross_weights: List[float] = []
+        self.cond_emb = None
+        self.residuals_in = None   # (9 skip residual tensors, mid residual, scale) produced by a ControlNet runner
+        self.stats_ws = torch.empty(batch * 64, dtype=torch.float32, device=self.dev)
+
+    # ------------------------------------------------------------------------------------------- buffers
+    def buf(self, name, shape) -> torch.Tensor:
+        t = self.ws.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=torch.float16, device=self.dev)
+            self.ws[name] = t
+        return t
+
+    def _lin(self, key, x2d, out, bias=None, residual=None, epilogue=L.EPI_NONE):
+        P = self.m.p
+        lo = self.lora.get(key)
+        if lo is None:
+            return ops.linear(x2d, P[key + ".w"], bias=bias, residual=residual, out=out, epilogue=epilogue)
+        A_cat, B2 = lo
+        t = ops.linear(x2d, A_cat, out=self.buf(f"lora_t.{A_cat.shape[0]}.{x2d.shape[0]}", (x2d.shape[0], A_cat.shape[0])))
+        return ops.linear(x2d, P[key + ".w"], bias=bias, residual=residual, out=out, epilogue=epilogue, lora=(t, B2))
+
+    # ------------------------------------------------------------------------------------------- per-call setup
+    def set_conditioning(self, timesteps, ctx: torch.Tensor, text_embeds: torch.Tensor, time_ids: torch.Tensor,
+                         extra_ctx: Optional[torch.Tensor] = None):
+        """Hoisted, step-invariant work (see module docstring).  ctx (B, L, D) [text tokens, then IP tokens if the
+        model has an IP adapter]; extra_ctx: further context rows appended for prompt-to-prompt mixed contexts."""
+        m, cfg, P, B = self.m, self.m.cfg, self.m.p, self.B
+        dev = self.dev
+        ts = torch.as_tensor(timesteps, dtype=torch.float32, device=dev).reshape(-1)
+        T = ts.numel()
+        t_sin = timestep_embedding(ts, cfg.block_out_channels[0]).half()
+        e = ops.linear(t_sin, P["time_embedding.linear_1.w"], bias=P["time_embedding.linear_1.b"], epilogue=L.EPI_SILU)
+        t_emb = ops.linear(e, P["time_embedding.linear_2.w"], bias=P["time_embedding.linear_2.b"])
+        tid = timestep_embedding(time_ids.to(dev).reshape(-1), cfg.addition_time_embed_dim).reshape(B, -1)
+        add_in = torch.cat([text_embeds.to(dev).float(), tid], dim=-1).half().contiguous()
+        a = ops.linear(add_in, P["add_embedding.linear_1.w"], bias=P["add_embedding.linear_1.b"], epilogue=L.EPI_SILU)
+        aug = ops.linear(a, P["add_embedding.linear_2.w"], bias=P["add_embedding.linear_2.b"])
+        emb = t_emb.float()[:, None, :] + aug.float()[None, :, :]               # (T, B, 1280)
+        act = torch.nn.functional.silu(emb).half().reshape(T * B, -1).contiguous()
+        self.temb_table = ops.linear(act, P["temb_all.w"], bias=P["temb_all.b"]).reshape(T, B, m.temb_cols)
+        self.set_context(ctx, extra_ctx)
+
+    def set_context(self, ctx: torch.Tensor, extra_ctx: Optional[torch.Tensor] = None):
+        """Project the cross-attention K/V of every attn2 layer once (text rows [+ mixed rows]; IP tokens)."""
+        m, P = self.m, self.m.p
+        ctx = ctx.to(self.dev, torch.float16)
+        n_ip = m.ip_tokens if m.ip is not None else 0
+        txt = ctx[:, : ctx.shape[1] - n_ip].contiguous()
+        if extra_ctx is not None:
+            txt = torch.cat([txt, extra_ctx.to(self.dev, torch.float16)], dim=0).contiguous()
+        self.ctx_txt = txt
+        self.ctx_rows, self.ctx_len = txt.shape[0], txt.shape[1]
+        txt2d = txt.reshape(-1, txt.shape[-1])
+        ip2d = ctx[:, ctx.shape[1] - n_ip:].contiguous().reshape(-1, ctx.shape[-1]) if n_ip else None
+        for name, ch, layers in m.tr_names:
+            for k in range(layers):
+                b = f"{name}.transformer_blocks.{k}"
+                kv = self.buf(b + ".kv", (self.ctx_rows, self.ctx_len, 2 * ch))
+                self._lin(b + ".attn2.kv", txt2d, kv.view(-1, 2 * ch))
+                self.kv[b] = kv
+                if n_ip:
+                    kvi = self.buf(b + ".kv_ip", (ctx.shape[0], n_ip, 2 * ch))
+                    ops.linear(ip2d, m.ip[b + ".attn2"], out=kvi.view(-1, 2 * ch))
+                    self.kv_ip[b] = kvi
+
+    def update_context_rows(self, row0: int, rows: torch.Tensor):
+        """Re-project K/V for context rows [row0, row0+n) only (prompt-to-prompt mixed contexts that change with the
+        step's alpha)."""
+        m = self.m
+        n = rows.shape[0]
+        self.ctx_txt[row0:row0 + n].copy_(rows)
+        x2d = self.ctx_txt[row0:row0 + n].reshape(-1, rows.shape[-1])
+        for name, ch, layers in m.tr_names:
+            for k in range(layers):
+                b = f"{name}.transformer_blocks.{k}"
+                self._lin(b + ".attn2.kv", x2d, self.kv[b][row0:row0 + n].view(-1, 2 * ch))
+
+    def set_controlnet_cond(self, cond: torch.Tensor):
+        """ControlNet conditioning embedding of the (constant) condition image (B,3,Himg,Wimg) in [0,1]: conv stack
+        of controlnet_cond_embedding [3P], run once per call."""
+        m, P, cfg = self.m, self.m.p, self.m.cfg
+        x = cond.to(self.dev, torch.float16).permute(0, 2, 3, 1)
+        x = torch.cat([x, x.new_zeros(*x.shape[:3], 5)], dim=3).contiguous()
+        h = self._silu(ops.conv3x3(x, P["cond.conv_in.w"], bias=P["cond.conv_in.b"]))
+        for i in range(2 * (len(cfg.cond_embed_channels) - 1)):
+            f = ops.conv3x3_s2 if i % 2 == 1 else ops.conv3x3
+            h = self._silu(f(h, P[f"cond.{i}.w"], bias=P[f"cond.{i}.b"]))
+        self.cond_emb = ops.conv3x3(h, P["cond.conv_out.w"], bias=P["cond.conv_out.b"])
+
+    @staticmethod
+    def _silu(t):
+        # once-per-call prologue (not on the per-step path)
+        return torch.nn.functional.silu(t.float()).half()
+
+    # ------------------------------------------------------------------------------------------- blocks
+    def _resblock(self, name, x, skip=None):
+        P, m = self.m.p, self.m
+        B, H, W, C1 = x.shape
+        C2 = 0 if skip is None else skip.shape[3]
+        cout = P[name + ".bias1"].shape[0]
+        a1 = ops.groupnorm(x, P[name + ".g1"], P[name + ".b1"], 1e-5, 1, x2=skip,
+                           out=self.buf(name + ".a1", (B, H, W, C1 + C2)), stats_ws=self.stats_ws)
+        off = m.temb_off[name]
+        h = ops.conv3x3(a1, P[name + ".w1"], bias=P[name + ".bias1"], rowvec=self.temb_step[:, off:off + cout],
+                        out=self.buf(name + ".h", (B, H, W, cout)))
+        a2 = ops.groupnorm(h, P[name + ".g2"], P[name + ".b2"], 1e-5, 1, out=self.buf(name + ".a2", (B, H, W, cout)),
+                           stats_ws=self.stats_ws)
+        out = self.buf(name + ".out", (B, H, W, cout))
+        if P[name + ".w2"].shape[1] > 9 * cout:
+            sc = [(x, 9 * cout)] + ([(skip, 9 * cout + C1)] if skip is not None else [])
+            return ops.conv3x3(a2, P[name + ".w2"], bias=P[name + ".bias2"], shortcut=sc, out=out)
+        return ops.conv3x3(a2, P[name + ".w2"], bias=P[name + ".bias2"], residual=x, out=out)
+
+    def _transformer(self, name, ch, layers, x, variant):
+        P, m = self.m.p, self.m
+        B, H, W, _ = x.shape
+        N = H * W
+        M = B * N
+        heads = ch // m.cfg.head_dim
+        scale = m.cfg.head_dim ** -0.5
+        n = ops.groupnorm(x, P[name + ".norm.g"], P[name + ".norm.b"], 1e-6, 0, out=self.buf(f"tr.n.{ch}.{N}", (B, H, W, ch)),
+                          stats_ws=self.stats_ws)
+        h = self.buf(f"tr.h.{ch}.{N}", (M, ch))
+        self._lin(name + ".proj_in", n.view(M, ch), h, bias=P[name + ".proj_in.b"])
+        ln = self.buf(f"tr.ln.{ch}.{N}", (M, ch))
+        qkv = self.buf(f"tr.qkv.{ch}.{N}", (B, N, 3 * ch))
+        q = self.buf(f"tr.q.{ch}.{N}", (B, N, ch))
+        o = self.buf(f"tr.o.{ch}.{N}", (B, N, ch))
+        g = self.buf(f"tr.g.{ch}.{N}", (M, 4 * ch))
+        self_replace = variant.get("self_replace", False) and N <= variant.get("self_threshold", 0)
+        ident = [(b, b, b, b) for b in range(B)]
+        self_items = variant["self_items"] if self_replace else ident
+        for k in range(layers):
+            b = f"{name}.transformer_blocks.{k}"
+            ops.layernorm(h, P[b + ".norm1.g"], P[b + ".norm1.b"], out=ln)
+            self._lin(b + ".attn1.qkv", ln, qkv.view(M, 3 * ch))
+            ops.attention(qkv, qkv, qkv, o, heads, N, N, self_items, 0, ch, 2 * ch, scale=scale)
+            self._lin(b + ".attn1.out", o.view(M, ch), h, bias=P[b + ".attn1.out.b"], residual=h)
+            ops.layernorm(h, P[b + ".norm2.g"], P[b + ".norm2.b"], out=ln)
+            self._lin(b + ".attn2.q", ln, q.view(M, ch))
+            kv = self.kv[b]
+            for ti, (items, wgt) in enumerate(zip(variant["cross_items"], variant["cross_weights"])):
+                ops.attention(q, kv, kv, o, heads, N, self.ctx_len, items, 0, 0, ch, scale=scale, out_weight=wgt,
+                              accumulate=ti > 0)
+            if m.ip is not None:
+                kvi = self.kv_ip[b]
+                ops.attention(q, kvi, kvi, o, heads, N, m.ip_tokens, ident, 0, 0, ch, scale=scale,
+                              out_weight=m.ip_scale, accumulate=True)
+            self._lin(b + ".attn2.out", o.view(M, ch), h, bias=P[b + ".attn2.out.b"], residual=h)
+            ops.layernorm(h, P[b + ".norm3.g"], P[b + ".norm3.b"], out=ln)
+            self._lin(b + ".ff1", ln, g, bias=P[b + ".ff1.b"], epilogue=L.EPI_GEGLU)
+            self._lin(b + ".ff2", g, h, bias=P[b + ".ff2.b"], residual=h)
+        out = self.buf(name + ".out", (B, H, W, ch))
+        self._lin(name + ".proj_out", h, out.view(M, ch), bias=P[name + ".proj_out.b"], residual=x.view(M, ch))
+        return out
+
+    def _encoder(self, h, variant):
+        m, cfg, P = self.m, self.m.cfg, self.m.p
+        skips = [h]
+        nb = len(cfg.block_out_channels)
+        for i in range(nb):
+            ch, layers = cfg.block_out_channels[i], cfg.transformer_layers[i]
+            for j in range(cfg.layers_per_block):
+                h = self._resblock(f"down_blocks.{i}.resnets.{j}", h)
+                if layers > 0:
+                    h = self._transformer(f"down_blocks.{i}.attentions.{j}", ch, layers, h, variant)
+                skips.append(h)
+            if i < nb - 1:
+                B, H, W, _ = h.shape
+                h = ops.conv3x3_s2(h, P[f"down{i}.w"], bias=P[f"down{i}.b"],
+                                   out=self.buf(f"down{i}.out", (B, H // 2, W // 2, ch)))
+                skips.append(h)
+        ch = cfg.block_out_channels[-1]
+        h = self._resblock("mid_block.resnets.0", h)
+        h = self._transformer("mid_block.attentions.0", ch, cfg.transformer_layers[-1], h, variant)
+        h = self._resblock("mid_block.resnets.1", h)
+        return h, skips
+
+    def _forward_unet(self, variant):
+        m, cfg, P = self.m, self.m.cfg, self.m.p
+        B, H, W = self.B, self.H, self.W
+        h = ops.conv3x3(self.sample_in, P["conv_in.w"], bias=P["conv_in.b"],
+                        out=self.buf("conv_in.out", (B, H, W, cfg.block_out_channels[0])))
+        h, skips = self._encoder(h, variant)
+        if variant.get("residuals", False):
+            down_r, mid_r, r_scale = self.residuals_in  # ControlNet outputs * conditioning_scale
+            skips = [ops.axpy(s, r, r_scale, out=self.buf(f"skip_add.{i}", tuple(s.shape))) for i, (s, r) in
+                     enumerate(zip(skips, down_r))]
+            h = ops.axpy(h, mid_r, r_scale, out=self.buf("mid_add", tuple(h.shape)))
+        nb = len(cfg.block_out_channels)
+        for i in range(nb):
+            ch, layers = cfg.block_out_channels[nb - 1 - i], cfg.transformer_layers[nb - 1 - i]
+            for j in range(cfg.layers_per_block + 1):
+                h = self._resblock(f"up_blocks.{i}.resnets.{j}", h, skips.pop())
+                if layers > 0:
+                    h = self._transformer(f"up_blocks.{i}.attentions.{j}", ch, layers, h, variant)
+            if i < nb - 1:
+                Bh, Hh, Wh, _ = h.shape
+                h = ops.upsample2x_conv3x3(h, P[f"up{i}.w"], bias=P[f"up{i}.b"],
+                                           out=self.buf(f"up{i}.out", (Bh, 2 * Hh, 2 * Wh, ch)))
+        a = ops.groupnorm(h, P["norm_out.g"], P["norm_out.b"], 1e-5, 1, out=self.buf("norm_out", tuple(h.shape)),
+                          stats_ws=self.stats_ws)
+        return ops.conv3x3(a, P["conv_out.w"], bias=P["conv_out.b"], out=self.buf("noise", (B, H, W, 8)))
+
+    def _forward_controlnet(self, variant):
+        m, cfg, P = self.m, self.m.cfg, self.m.p
+        B, H, W = self.B, self.H, self.W
+        c0 = cfg.block_out_channels[0]
+        # sample = conv_in(sample) + cond_embedding: the embedding is the GEMM epilogue residual
+        h = ops.conv3x3(self.sample_in, P["conv_in.w"], bias=P["conv_in.b"], residual=self.cond_emb,
+                        out=self.buf("conv_in.out", (B, H, W, c0)))
+        h, skips = self._encoder(h, variant)
+        outs = []
+        for i, s in enumerate(skips):
+            Bs, Hs, Ws, Cs = s.shape
+            o = self.buf(f"zero{i}.out", (Bs, Hs, Ws, Cs))
+            ops.linear(s.view(-1, Cs), P[f"zero{i}.w"], bias=P[f"zero{i}.b"], out=o.view(-1, Cs))
+            outs.append(o)
+        Bs, Hs, Ws, Cs = h.shape
+        mid = self.buf("zero_mid.out", (Bs, Hs, Ws, Cs))
+        ops.linear(h.view(-1, Cs), P["zero_mid.w"], bias=P["zero_mid.b"], out=mid.view(-1, Cs))
+        return outs, mid
+
+    # ------------------------------------------------------------------------------------------- public
+    def default_variant(self) -> dict:
+        ident = [(b, b, b, b) for b in range(self.B)]
+        return {"self_replace": False, "self_threshold": 0, "self_items": ident, "cross_items": [ident],
+                "cross_weights": [1.0], "residuals": False}
+
+    def forward(self, step_index: int, variant: Optional[dict] = None, key: Optional[tuple] = None):
+        """Run one forward for the timestep `step_index` of the schedule given to set_conditioning.  The input is
+        whatever self.sample_in holds; returns the (persistent) output buffer(s)."""
+        variant = variant or self.default_variant()
+        self.temb_step.copy_(self.temb_table[step_index])
+        fn = self._forward_controlnet if self.m.controlnet else self._forward_unet
+        if not self.use_graphs or key is None:
+            return fn(variant)
+        if key in self.graphs:
+            self.graphs[key].replay()
+            return self._out[key]
+        if key not in self.warm:
+            self.warm.add(key)
+            self._out = getattr(self, "_out", {})
+            self._out[key] = fn(variant)  # eager run: allocates buffers, sets kernel attributes
+            return self._out[key]
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            self._out[key] = fn(variant)
+        self.graphs[key] = g
+        g.replay()
+        return self._out[key]
