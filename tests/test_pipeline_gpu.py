@@ -1,0 +1,166 @@
+"""GPU parity of the full two-stage loops (LoRA and InstantID variants) against oracle.pipeline.denoise on the tiny
+topology: 18 steps so that the fusion window (step index > 15) is exercised, P2P self-replace threshold 8x8 tokens,
+two concepts with disjoint masks.  Final-latent tolerance 2e-2 relative (18 chained UNet calls in fp16)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from util_models import lora, ocfg, oracle_lora, r16, rel, weights  # noqa: E402
+
+STEPS = 18
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _masks(size):
+    m1 = torch.zeros(size, size)
+    m2 = torch.zeros(size, size)
+    m1[size // 8: 7 * size // 8, size // 16: 7 * size // 16] = 1
+    m2[size // 8: 7 * size // 8, 9 * size // 16: 15 * size // 16] = 1
+    return m1, m2
+
+
+def test_lora_two_stage_pipeline():
+    from omg_b200.config import UNetConfig
+    from omg_b200.pipelines import ConceptModels, LoraMultiConceptPipeline, revise_regionally_controlnet_forward
+    from omg_b200.prompt_attention import AttentionReplace
+    from omg_b200.unet import PackedUNet
+    from oracle import p2p as op2p
+    from oracle import unet as ou
+    from oracle.pipeline import Concept, denoise
+    cfg = UNetConfig.tiny()
+    sd = weights(cfg, 0)
+    size = 256
+    prompt = "a man and a woman on the beach"
+    prompts = [prompt] * 2
+    regions = [("a man smiling", "blurry"), ("a woman smiling", "blurry")]
+    pipe = LoraMultiConceptPipeline(PackedUNet(cfg, sd))
+    controller = AttentionReplace(prompts, 50, {"default_": 1.0}, 0.4, width=8, height=8)
+    revise_regionally_controlnet_forward(pipe, controller)
+    cm = ConceptModels(PackedUNet(cfg, sd))
+    loras = [lora(cfg, 101), lora(cfg, 102)]
+    cm.load_lora_weights(loras[0], adapter_name="manA")
+    cm.load_lora_weights(loras[1], adapter_name="womanB")
+    g = torch.Generator().manual_seed(14)
+    lat0 = torch.randn(1, 4, size // 8, size // 8, generator=g).half()
+    masks = list(_masks(size))
+    common = dict(prompt=[prompts, regions], negative_prompt=["noisy"] * 2, guidance_scale=7.5,
+                  num_inference_steps=STEPS, cross_attention_kwargs={"scale": 0.8}, concept_models=cm,
+                  lora_list=["manA", "womanB"], styleL=False, height=size, width=size, output_type="latent",
+                  latents=lat0)
+    out1 = pipe(stage=1, **common).images
+    assert controller.cur_step == STEPS
+    controller.reset()
+    out2 = pipe(stage=2, region_masks=masks, **common).images
+    assert torch.equal(out1[0], out1[1])                      # stage 1: both rows identical trajectories
+    assert torch.equal(out2[0], out1[0])                      # image 0 of stage 2 reproduces the layout image
+    assert not torch.equal(out2[1], out2[0])
+
+    # ---- oracle
+    pe, ne, pp, np_ = pipe.encode_prompt(prompts, ["noisy"] * 2, 0.8)
+    ctx4, pooled4 = r16(torch.cat([ne, pe])), r16(torch.cat([np_, pp]))
+    tid = torch.tensor([[size, size, 0, 0, size, size]], dtype=torch.float32)
+    octrl = op2p.AttentionReplaceOracle(prompts, 50, {"default_": 1.0}, 0.4, 8, 8)
+    octrl.num_att_layers = len(ou.attention_names(ocfg(cfg)))
+    main = ou.Ctx(sd, ocfg(cfg), attn_core=ou.make_p2p_attn_core(octrl))
+    concepts = []
+    for k, (rp, rn) in enumerate(regions):
+        e, n_, p_, np2 = cm.encode_prompt(rp, negative_prompt=rn)
+        concepts.append(Concept(r16(torch.cat([n_, e])), r16(torch.cat([np2, p_])), tid.repeat(2, 1), masks[k],
+                                unet=ou.Ctx(sd, ocfg(cfg), lora=oracle_lora([(loras[k], 1.0)], 0.8))))
+    ref2 = denoise(main, lat0.float(), ctx4, pooled4, tid.repeat(4, 1), concepts, 2, STEPS, 7.5)
+    e0, e1 = rel(out2[0], ref2[0]), rel(out2[1], ref2[1])
+    print("lora pipeline final-latent rel err: layout", e0, "fused", e1)
+    assert e0 < 2e-2 and e1 < 2e-2
+
+
+def test_lora_pipeline_skips_concept_without_mask_and_style_adapter():
+    from omg_b200.config import UNetConfig
+    from omg_b200.pipelines import ConceptModels, LoraMultiConceptPipeline
+    from omg_b200.unet import PackedUNet
+    from oracle import unet as ou
+    from oracle.pipeline import Concept, denoise
+    cfg = UNetConfig.tiny()
+    sd = weights(cfg, 0)
+    size = 128
+    pipe = LoraMultiConceptPipeline(PackedUNet(cfg, sd))           # no controller installed: plain attention
+    cm = ConceptModels(PackedUNet(cfg, sd))
+    loras = {"a": lora(cfg, 201), "b": lora(cfg, 202), "style": lora(cfg, 203)}
+    for k, v in loras.items():
+        cm.load_lora_weights(v, adapter_name=k)
+    g = torch.Generator().manual_seed(3)
+    lat0 = torch.randn(1, 4, size // 8, size // 8, generator=g).half()
+    m1, _ = _masks(size)
+    regions = [("x", "y"), ("z", "w")]
+    out = pipe(prompt=[["p"] * 2, regions], negative_prompt=["n"] * 2, guidance_scale=5.0, num_inference_steps=STEPS,
+               cross_attention_kwargs={"scale": 0.8}, concept_models=cm, lora_list=["a", "b"], styleL=True, stage=2,
+               region_masks=[m1, None], height=size, width=size, output_type="latent", latents=lat0).images
+    pe, ne, pp, np_ = pipe.encode_prompt(["p"] * 2, ["n"] * 2)
+    tid = torch.tensor([[size, size, 0, 0, size, size]], dtype=torch.float32)
+    concepts = []
+    for k, (rp, rn) in enumerate(regions):
+        e, n_, p_, np2 = cm.encode_prompt(rp, negative_prompt=rn)
+        lo = oracle_lora([(loras["ab"[k]], 0.7), (loras["style"], 0.5)], 0.8)
+        concepts.append(Concept(r16(torch.cat([n_, e])), r16(torch.cat([np2, p_])), tid.repeat(2, 1),
+                                m1 if k == 0 else None, unet=ou.Ctx(sd, ocfg(cfg), lora=lo)))
+    ref = denoise(ou.Ctx(sd, ocfg(cfg)), lat0.float(), r16(torch.cat([ne, pe])), r16(torch.cat([np_, pp])),
+                  tid.repeat(4, 1), concepts, 2, STEPS, 5.0)
+    e = rel(out, ref)
+    print("style/None-mask pipeline rel err", e)
+    assert e < 2e-2
+
+
+def test_instantid_two_stage_pipeline():
+    from omg_b200 import synthetic
+    from omg_b200.config import UNetConfig
+    from omg_b200.pipelines import ConceptModels, InstantidMultiConceptPipeline, revise_regionally_controlnet_forward
+    from omg_b200.prompt_attention import AttentionReplace
+    from omg_b200.unet import PackedUNet
+    from oracle import p2p as op2p
+    from oracle import unet as ou
+    from oracle.pipeline import Concept, denoise
+    from oracle.resampler import resampler_forward
+    cfg = UNetConfig.tiny()
+    sd = weights(cfg, 0)
+    idsd = weights(cfg, 41, controlnet=True)
+    size = 128
+    rs = torch.load(os.path.join(G, "resampler.pt"))
+    ipw = {k: (r16(a), r16(b)) for k, (a, b) in synthetic.make_ip_adapter(cfg, 31).items()}
+    pipe = InstantidMultiConceptPipeline(PackedUNet(cfg, sd), controlnet=PackedUNet(cfg, idsd, controlnet=True))
+    prompts = ["two people"] * 2
+    controller = AttentionReplace(prompts, 50, {"default_": 1.0}, 0.4, width=4, height=4)
+    revise_regionally_controlnet_forward(pipe, controller)
+    cm = ConceptModels(PackedUNet(cfg, sd))
+    cm.load_ip_adapter_instantid(rs["sd"], ipw, heads=rs["heads"], dim_head=rs["dim_head"], num_tokens=16)
+    cm.set_ip_adapter_scale(0.8)
+    g = torch.Generator().manual_seed(53)
+    lat0 = torch.randn(1, 4, size // 8, size // 8, generator=g).half()
+    faces = [torch.nn.functional.normalize(torch.randn(512, generator=g), dim=0) for _ in range(2)]
+    kps = r16(torch.rand(3, size, size, generator=g))
+    masks = list(_masks(size))
+    regions = [("a man", "bad", None), ("a woman", "bad", None)]
+    out = pipe(prompt=[prompts, regions], negative_prompt=["noisy"] * 2, guidance_scale=3.0,
+               num_inference_steps=STEPS, concept_models=cm, stage=2, region_masks=masks, image=kps,
+               controlnet_conditioning_scale=0.8, face_embeds=faces, height=size, width=size, output_type="latent",
+               latents=lat0).images
+    pe, ne, pp, np_ = pipe.encode_prompt(prompts, ["noisy"] * 2)
+    tid = torch.tensor([[size, size, 0, 0, size, size]], dtype=torch.float32)
+    octrl = op2p.AttentionReplaceOracle(prompts, 50, {"default_": 1.0}, 0.4, 4, 4)
+    octrl.num_att_layers = len(ou.attention_names(ocfg(cfg)))
+    main = ou.Ctx(sd, ocfg(cfg), attn_core=ou.make_p2p_attn_core(octrl))
+    concepts = []
+    for k, reg in enumerate(regions):
+        e, n_, p_, np2 = pipe.encode_prompt(reg[0], reg[1])
+        emb = faces[k].reshape(1, 1, 512)
+        tokens = resampler_forward(rs["sd"], torch.cat([torch.zeros_like(emb), emb]), rs["heads"], rs["dim_head"])
+        concepts.append(Concept(r16(torch.cat([n_, e])), r16(torch.cat([np2, p_])), tid.repeat(2, 1), masks[k],
+                                unet=ou.Ctx(sd, ocfg(cfg), ip_weights=ipw, ip_tokens=16, ip_scale=0.8),
+                                image_tokens=r16(tokens)))
+    ref = denoise(main, lat0.float(), r16(torch.cat([ne, pe])), r16(torch.cat([np_, pp])), tid.repeat(4, 1), concepts,
+                  2, STEPS, 3.0, identitynet=ou.Ctx(idsd, ocfg(cfg)), identity_cond=kps[None].repeat(2, 1, 1, 1),
+                  identity_scale=0.8)
+    e = rel(out, ref)
+    print("instantid pipeline final-latent rel err", e)
+    assert e < 2e-2
