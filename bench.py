@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the OMG two-stage SDXL denoising hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is ONE IMAGE through the whole hot path as the reference executes it (config 2): stage 1 (30 steps, main
+UNet B=4) + stage 2 (30 steps, main UNet B=4, and for step index > 15 two concept UNets B=2 with un-merged LoRA) =
+296 UNet sample-forwards at 128x128 latents, latents out (no VAE / text encoders / segmentation: SURVEY section 8).
+
+* value: images/sec with every input already resident in HBM (device tensors in, device latents out).
+* e2e:   the same through the public pipeline call with HOST buffers (pinned prompt embeddings, masks, initial noise
+         copied H2D inside the timed region; final latents copied D2H).
+* roofline: the dominant kernel is gemm_tc_kernel (every conv / linear: ~88 % of the FLOPs).  After the timed region
+  one main-UNet forward is replayed eagerly with a CUDA-event pair around every launch of that kernel; achieved =
+  sum(algorithmic FLOPs) / sum(durations).
+* cpu_baseline: the fp32 oracle (a port of the reference's diffusers path) timed on the host cores for one
+  sample-forward at the same latent size, extrapolated to images/sec (= 1 / (296 * t)).
+N > 1: independent images, one replica per GPU (weights broadcast once over NCCL, final latents all-gathered);
+scaling is weak (K images per GPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SAMPLE_FORWARDS_PER_IMAGE = 296  # 30*4 (stage 1) + 30*4 + 14*2*2 (stage 2), BASELINE.md section 3
+STEPS_PER_STAGE = 30
+IMAGE = 1024
+
+
+def read_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        os.unlink(self.f.name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample_forward_seconds(cfg, sd_cpu, latent, threads, reps=1):
+    """Time oracle.unet.unet_forward (fp32, B=1) on the host cores.  The oracle is the checker; this is its one
+    sanctioned use as a measured baseline."""
+    from oracle import unet as ou
+    ocfg = ou.UNetConfig(block_out_channels=cfg.block_out_channels, transformer_layers=cfg.transformer_layers,
+                         cross_attention_dim=cfg.cross_attention_dim, addition_time_embed_dim=cfg.addition_time_embed_dim,
+                         pooled_dim=cfg.pooled_dim, cond_embed_channels=cfg.cond_embed_channels)
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 4, latent, latent, generator=g)
+    ctx = torch.randn(1, 77, cfg.cross_attention_dim, generator=g)
+    pooled = torch.randn(1, cfg.pooled_dim, generator=g)
+    tid = torch.tensor([[IMAGE, IMAGE, 0, 0, IMAGE, IMAGE]], dtype=torch.float32)
+    c = ou.Ctx(sd_cpu, ocfg)
+    best = 1e30
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            ou.unet_forward(c, x, 500.0, ctx, pooled, tid)
+            best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def cpu_state_dict(cfg, device):
+    from omg_b200 import synthetic
+    if torch.cuda.is_available():
+        sd = synthetic.make_state_dict(cfg, seed=0, device=device, dtype=torch.float16)
+        return {k: v.float().cpu() for k, v in sd.items()}
+    return synthetic.make_state_dict(cfg, seed=0, device="cpu", dtype=torch.float32)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU path for this metric.  diffusers/peft/xformers are not installable
+    here, so this is the fp32 oracle port timed on the host cores; each step = one UNet sample-forward at the
+    workload's latent size (a bounded sample of the 296 an image needs)."""
+    if rank != 0:
+        return
+    from omg_b200.config import UNetConfig
+    cfg = UNetConfig.sdxl()
+    threads = os.cpu_count() or 1
+    sd = cpu_state_dict(cfg, "cuda:0" if torch.cuda.is_available() else "cpu")
+    latent = IMAGE // 8
+    for _ in range(args.warmup):
+        cpu_sample_forward_seconds(cfg, sd, latent, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_sample_forward_seconds(cfg, sd, latent, threads)
+    per = (time.perf_counter() - t0) / args.steps
+    value = 1.0 / (SAMPLE_FORWARDS_PER_IMAGE * per)
+    sample = (f"{args.steps} x one fp32 UNet sample-forward at 128x128 latents (6.76 TFLOP each) on {threads} host "
+              f"threads; images/s extrapolated as 1/(296 x {per:.2f} s)")
+    print(json.dumps({
+        "impl": "reference", "metric": "1024^2 images/sec @30 steps, 2 concepts", "value": value,
+        "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "images/sec", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE config 2: SDXL UNet (random-init, 2.57 G params), 1024x1024 (latent 128x128), two-stage "
+                        "OMG loop, 30 steps per stage, 2 LoRA concepts (rank 32 on every transformer Linear), guidance "
+                        "7.5, prompt-to-prompt AttentionReplace(50, cross 1.0, self 0.4), as-executed 296 UNet "
+                        "sample-forwards per image",
+            "images_per_gpu_per_step": 1, "parallelism": f"dp{n_gpus} (independent images, weight replicas)",
+            "l2_policy": "inputs+weights (5.1 GB) exceed the 126 MB L2; no flush needed between steps"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch.distributed as dist
+    from omg_b200 import _lib, factory, ops, synthetic
+    from omg_b200.config import UNetConfig, unet_flops
+    from omg_b200 import unet as unet_mod
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    _lib.load()
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    cfg = UNetConfig.sdxl()
+
+    # weights: generated on rank 0, broadcast once over NCCL (the only collective besides the final gather)
+    t_b0 = time.perf_counter()
+    sd = synthetic.make_state_dict(cfg, seed=0, device=dev, dtype=torch.float16)
+    if world > 1:
+        for k in sorted(sd):
+            dist.broadcast(sd[k], src=0)
+        torch.cuda.synchronize()
+    t_bcast = time.perf_counter() - t_b0
+    wl = factory.build_lora_workload(cfg, IMAGE, 2, 32, STEPS_PER_STAGE, 7.5, device=dev, state_dict=sd)
+    del sd
+    pipe = wl.pipe
+    kw = dict(wl.call_kwargs)
+    prompts, regions = kw["prompt"]
+    # text-encoder outputs (outside the hot path) prepared once: host pinned copies for e2e, device copies for value
+    pe, ne, pp, np_ = pipe.encode_prompt(prompts, kw["negative_prompt"], 0.8)
+    reg = [wl.concept_models.encode_prompt(r[0], negative_prompt=r[1]) for r in regions]
+    host = {"pe": pe.half().pin_memory(), "ne": ne.half().pin_memory(), "pp": pp.half().pin_memory(),
+            "np": np_.half().pin_memory(), "reg": [tuple(t.half().pin_memory() for t in r) for r in reg],
+            "masks": [m.pin_memory() for m in wl.masks]}
+    devt = {"pe": host["pe"].to(dev), "ne": host["ne"].to(dev), "pp": host["pp"].to(dev), "np": host["np"].to(dev),
+            "reg": [tuple(t.to(dev) for t in r) for r in host["reg"]], "masks": [m.to(dev) for m in host["masks"]]}
+    h2d = sum(t.numel() * t.element_size() for t in [host["pe"], host["ne"], host["pp"], host["np"]]) * 2
+    h2d += sum(t.numel() * t.element_size() for r in host["reg"] for t in r)
+    h2d += sum(m.numel() * m.element_size() for m in host["masks"])
+    lat_bytes = 4 * (IMAGE // 8) ** 2 * 2
+    h2d += 2 * lat_bytes
+    d2h = 2 * 2 * lat_bytes
+
+    def one_image(seed, src, to_host):
+        """inference_lora.py:262-297 flow: stage 1 -> stage 2 from the same seed; masks are inputs."""
+        g = torch.Generator().manual_seed(seed)
+        noise = torch.randn(1, 4, IMAGE // 8, IMAGE // 8, generator=g).half()
+        if src is host:
+            noise = noise.pin_memory()
+        common = dict(kw, prompt_embeds=src["pe"], negative_prompt_embeds=src["ne"], pooled_prompt_embeds=src["pp"],
+                      negative_pooled_prompt_embeds=src["np"], region_prompt_embeds=src["reg"])
+        o1 = pipe(stage=1, latents=noise.to(dev, non_blocking=True), **common).images
+        wl.controller.reset()
+        o2 = pipe(stage=2, latents=noise.to(dev, non_blocking=True), region_masks=src["masks"], **common).images
+        wl.controller.reset()
+        if to_host:
+            return o1.cpu(), o2.cpu()
+        return o1, o2
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(k, src, to_host):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        outs = [one_image(14 + rank * 1000 + i, src, to_host) for i in range(k)]
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), outs
+
+    for i in range(args.warmup):
+        one_image(14, devt, False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = unet_mod.total_kernel_launches()
+    ms, outs = timed(args.steps, devt, False)
+    launches = unet_mod.total_kernel_launches() - n0
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, outs_h = timed(args.steps, host, True)
+    if world > 1:  # gather final latents (128 KiB per image) on every rank
+        mine = torch.stack([o[1] for o in outs]).to(dev)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+    finite = all(bool(torch.isfinite(o[1]).all()) for o in outs)
+
+    if rank == 0:
+        imgs = args.steps * world
+        value = imgs / (ms / 1e3)
+        e2e = imgs / (ms_e2e / 1e3)
+        peaks = read_peaks()
+        # ---- roofline of the dominant kernel (gemm_tc_kernel), measured live with CUDA events
+        prof = []
+        orig = ops.gemm
+
+        def prof_gemm(a_views, segs, w, N, Ktot, d_view, **kws):
+            pix = d_view.W * d_view.H * d_view.B
+            k_total = sum(s[4] for s in segs)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            orig(a_views, segs, w, N, Ktot, d_view, **kws)
+            e1.record()
+            prof.append((2.0 * pix * N * k_total, e0, e1))
+
+        main_runner = next(r for k, r in pipe._runners.items() if k[0] == "main")
+        ops.gemm = prof_gemm
+        try:
+            main_runner.forward(0, main_runner.default_variant(), key=None)
+        finally:
+            ops.gemm = orig
+        torch.cuda.synchronize()
+        g_flops = sum(p[0] for p in prof)
+        g_ms = sum(p[1].elapsed_time(p[2]) for p in prof)
+        achieved = g_flops / g_ms / 1e9 if g_ms > 0 else 0.0
+        peak = peaks["bf16_tflops_sustained"] if peaks else 1400.0
+        flops_img = SAMPLE_FORWARDS_PER_IMAGE * unet_flops(cfg, IMAGE // 8, IMAGE // 8)
+        out = {
+            "metric": "1024^2 images/sec @30 steps, 2 concepts", "value": value, "unit": "images/sec",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": e2e, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None, "kernel": "gemm_tc_kernel",
+                         "launches_profiled": len(prof),
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback"},
+            "unet_step_ms": {"main_b4": None},
+            "whole_path_tflops": flops_img * imgs / (ms / 1e3) / 1e12 / world,
+            "weight_broadcast_s": t_bcast, "finite": finite,
+        }
+        # UNet step ms (BASELINE metric ii): one graph replay of the main B=4 UNet
+        sync_all() if world == 1 else torch.cuda.synchronize()
+        key = next(iter(main_runner.graphs)) if main_runner.graphs else None
+        if key is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                main_runner.graphs[key].replay()
+            e1.record()
+            torch.cuda.synchronize()
+            out["unet_step_ms"]["main_b4"] = e0.elapsed_time(e1) / 5
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            sd_cpu = cpu_state_dict(cfg, dev)
+            t = cpu_sample_forward_seconds(cfg, sd_cpu, IMAGE // 8, threads)
+            out["cpu_baseline"] = {"value": 1.0 / (SAMPLE_FORWARDS_PER_IMAGE * t), "unit": "images/sec",
+                                   "cores": threads, "kind": "port",
+                                   "sample": f"one fp32 oracle UNet sample-forward at 128x128 latents took {t:.2f} s on "
+                                             f"{threads} host threads; an image needs 296 of them (extrapolated)"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

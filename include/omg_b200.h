@@ -100,9 +100,12 @@ int omg_attention(const omg_attn_desc* desc, void* stream);
 
 /*
  * GroupNorm(32 groups) over channels-last fp16, optional SiLU, input = channel-concatenation of (x1 | x2).
- * y[B, HW, C1+C2].  stats_ws: B*64 floats of scratch.  Replaces torch GroupNorm + SiLU + torch.cat inside diffusers
+ * y[B, HW, C1+C2].  stats_ws: OMG_GN_WS_FLOATS(B) floats of scratch.  Deterministic: no atomics, results do not depend
+ * on the batch position of an image.  Replaces torch GroupNorm + SiLU + torch.cat inside diffusers
  * ResnetBlock2D / Transformer2DModel / UNet up-blocks [3P] (call site src/pipelines/lora_pipeline.py:546-566).
  */
+#define OMG_GN_MAX_SPLITS 256
+#define OMG_GN_WS_FLOATS(B) ((B) * 64 * (OMG_GN_MAX_SPLITS + 1))
 int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, const void* gamma, const void* beta,
                   float eps, int silu, void* stats_ws, void* y, void* stream);
 

@@ -24,15 +24,13 @@ __device__ __forceinline__ uint4 gn_load8(const GnSrc& s, size_t pix, int c) {
     return *reinterpret_cast<const uint4*>(s.x2 + pix * s.C2 + (c - s.C1));
 }
 
-// stats[b][g] = {sum, sumsq}.  grid = (row_splits, B); block = (C/8, rows_par)
-__global__ void gn_stats_kernel(GnSrc s, int HW, int cpg, int rows_per_cta, float* __restrict__ stats) {
-    __shared__ float s_sum[32], s_sq[32];
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    if (tid < 32) {
-        s_sum[tid] = 0.f;
-        s_sq[tid] = 0.f;
-    }
-    __syncthreads();
+// Deterministic (atomic-free, batch-invariant) statistics:
+//   pass 1  partial[b][split][g] = {sum, sumsq} over the CTA's rows    grid = (splits, B), block = (C/8, rows_par)
+//   pass 2  stats[b][g] = {mean, rstd}, partials summed in split order  grid = B, block = 32
+// Identical images in a batch therefore get bit-identical results (the reference's stage-1 rows are identical).
+__global__ void gn_partial_kernel(GnSrc s, int HW, int cpg, int rows_per_cta, float* __restrict__ partial) {
+    extern __shared__ float s_red[];  // [rows_par][C] sums, then [rows_par][C] squares
+    const int C = s.C1 + s.C2;
     const int b = blockIdx.y;
     const int c = threadIdx.x * 8;
     const int r0 = blockIdx.x * rows_per_cta;
@@ -52,32 +50,57 @@ __global__ void gn_stats_kernel(GnSrc s, int HW, int cpg, int rows_per_cta, floa
             q[2 * i + 1] += f.y * f.y;
         }
     }
-    // fold the 8 channels into (at most two) groups, then into the CTA accumulators
-    int g_prev = c / cpg;
-    float ps = 0.f, pq = 0.f;
+    float* s_sum = s_red;
+    float* s_sq = s_red + blockDim.y * C;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int g = (c + i) / cpg;
-        if (g != g_prev) {
-            atomicAdd(&s_sum[g_prev], ps);
-            atomicAdd(&s_sq[g_prev], pq);
-            ps = pq = 0.f;
-            g_prev = g;
-        }
-        ps += a[i];
-        pq += q[i];
+        s_sum[threadIdx.y * C + c + i] = a[i];
+        s_sq[threadIdx.y * C + c + i] = q[i];
     }
-    atomicAdd(&s_sum[g_prev], ps);
-    atomicAdd(&s_sq[g_prev], pq);
     __syncthreads();
+    if (threadIdx.y == 0) {  // fold the row-parallel copies in a fixed order
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float sa = a[i], sq = q[i];
+            for (int y = 1; y < blockDim.y; ++y) {
+                sa += s_sum[y * C + c + i];
+                sq += s_sq[y * C + c + i];
+            }
+            s_sum[c + i] = sa;
+            s_sq[c + i] = sq;
+        }
+    }
+    __syncthreads();
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     if (tid < 32) {
-        atomicAdd(&stats[((size_t)b * 32 + tid) * 2], s_sum[tid]);
-        atomicAdd(&stats[((size_t)b * 32 + tid) * 2 + 1], s_sq[tid]);
+        float sa = 0.f, sq = 0.f;
+        for (int k = 0; k < cpg; ++k) {
+            sa += s_sum[tid * cpg + k];
+            sq += s_sq[tid * cpg + k];
+        }
+        float* o = partial + (((size_t)b * gridDim.x + blockIdx.x) * 32 + tid) * 2;
+        o[0] = sa;
+        o[1] = sq;
     }
 }
 
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int splits, float inv_n, float eps,
+                                   float* __restrict__ stats) {
+    const int b = blockIdx.x, g = threadIdx.x;
+    float sa = 0.f, sq = 0.f;
+    for (int k = 0; k < splits; ++k) {
+        const float* p = partial + (((size_t)b * splits + k) * 32 + g) * 2;
+        sa += p[0];
+        sq += p[1];
+    }
+    const float mean = sa * inv_n;
+    const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
+    stats[((size_t)b * 32 + g) * 2] = mean;
+    stats[((size_t)b * 32 + g) * 2 + 1] = rsqrtf(var + eps);
+}
+
 // grid = (ceil(HW*C/8 / 256), B)
-__global__ void gn_apply_kernel(GnSrc s, int HW, int cpg, float eps, int silu, const float* __restrict__ stats,
+__global__ void gn_apply_kernel(GnSrc s, int HW, int cpg, int silu, const float* __restrict__ stats,
                                 const __half* __restrict__ gamma, const __half* __restrict__ beta,
                                 __half* __restrict__ y) {
     const int C = s.C1 + s.C2;
@@ -93,7 +116,6 @@ __global__ void gn_apply_kernel(GnSrc s, int HW, int cpg, float eps, int silu, c
     const __half* xh = reinterpret_cast<const __half*>(&u);
     const __half* gh = reinterpret_cast<const __half*>(&gw);
     const __half* bh = reinterpret_cast<const __half*>(&bw);
-    const float inv_n = 1.0f / ((float)HW * (float)cpg);
     float out[8];
     int g_cur = -1;
     float mean = 0.f, rstd = 0.f;
@@ -102,10 +124,8 @@ __global__ void gn_apply_kernel(GnSrc s, int HW, int cpg, float eps, int silu, c
         const int g = (c + i) / cpg;
         if (g != g_cur) {
             g_cur = g;
-            const float sm = stats[((size_t)b * 32 + g) * 2], sq = stats[((size_t)b * 32 + g) * 2 + 1];
-            mean = sm * inv_n;
-            const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
-            rstd = rsqrtf(var + eps);
+            mean = stats[((size_t)b * 32 + g) * 2];
+            rstd = stats[((size_t)b * 32 + g) * 2 + 1];
         }
         float v = (__half2float(xh[i]) - mean) * rstd * __half2float(gh[i]) + __half2float(bh[i]);
         if (silu) v = v / (1.0f + __expf(-v));
@@ -196,27 +216,36 @@ extern "C" int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int
     const int C = C1 + C2;
     OMG_CHECK(x1 && gamma && beta && stats_ws && y, "omg_groupnorm: null pointer");
     OMG_CHECK(C1 > 0 && C1 % 8 == 0 && C2 >= 0 && C2 % 8 == 0 && (C2 == 0 || x2), "omg_groupnorm: bad channel split");
-    OMG_CHECK(C % 32 == 0 && C / 8 <= 1024, "omg_groupnorm: C=%d must be a multiple of 32 and <= 8192", C);
+    OMG_CHECK(C % 32 == 0 && C <= 2560, "omg_groupnorm: C=%d must be a multiple of 32 and <= 2560", C);
     OMG_CHECK(B >= 1 && HW >= 1, "omg_groupnorm: empty input");
     const int cpg = C / 32;
     GnSrc s{static_cast<const __half*>(x1), static_cast<const __half*>(x2), C1, C2};
-    OMG_CUDA(cudaMemsetAsync(stats_ws, 0, (size_t)B * 32 * 2 * sizeof(float), stream));
     const int tx = C / 8;
     int ty = 1024 / tx;
     if (ty > 16) ty = 16;
     if (ty < 1) ty = 1;
-    // enough CTAs to fill the machine: ~4 per SM across the batch
+    // enough CTAs to fill the machine: ~4 per SM across the batch, at most OMG_GN_MAX_SPLITS per image
     int splits = (148 * 4 + B - 1) / B;
+    if (splits > OMG_GN_MAX_SPLITS) splits = OMG_GN_MAX_SPLITS;
     int rows_per_cta = (HW + splits - 1) / splits;
     if (rows_per_cta < ty) rows_per_cta = ty;
     splits = (HW + rows_per_cta - 1) / rows_per_cta;
-    gn_stats_kernel<<<dim3(splits, B), dim3(tx, ty), 0, stream>>>(s, HW, cpg, rows_per_cta,
-                                                                   static_cast<float*>(stats_ws));
-    if (check_launch("gn_stats_kernel")) return 1;
+    float* stats = static_cast<float*>(stats_ws);             // [B][32][2] mean, rstd
+    float* partial = stats + (size_t)B * 64;                  // [B][splits][32][2]
+    const size_t smem = (size_t)2 * ty * C * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        OMG_CUDA(cudaFuncSetAttribute(gn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4));  // ty * C <= 1024 * 8
+        configured = true;
+    }
+    gn_partial_kernel<<<dim3(splits, B), dim3(tx, ty), smem, stream>>>(s, HW, cpg, rows_per_cta, partial);
+    if (check_launch("gn_partial_kernel")) return 1;
+    gn_finalize_kernel<<<B, 32, 0, stream>>>(partial, splits, 1.0f / ((float)HW * (float)cpg), eps, stats);
+    if (check_launch("gn_finalize_kernel")) return 1;
     const size_t nvec = (size_t)HW * (C / 8);
     gn_apply_kernel<<<dim3((unsigned)((nvec + 255) / 256), B), 256, 0, stream>>>(
-        s, HW, cpg, eps, silu, static_cast<const float*>(stats_ws), static_cast<const __half*>(gamma),
-        static_cast<const __half*>(beta), static_cast<__half*>(y));
+        s, HW, cpg, silu, stats, static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
+        static_cast<__half*>(y));
     return check_launch("gn_apply_kernel");
 }
 

@@ -34,6 +34,17 @@ def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
     return torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1)
 
 
+# kernels executed through CUDA-graph replays (the C-ABI launch counter only sees direct launches; a capture counts
+# once there and is not executed)
+REPLAYED_LAUNCHES = [0]
+CAPTURED_LAUNCHES = [0]
+
+
+def total_kernel_launches() -> int:
+    """Kernels of this library executed so far: direct launches + launches inside replayed graphs."""
+    return L.launch_count() - CAPTURED_LAUNCHES[0] + REPLAYED_LAUNCHES[0]
+
+
 class PackedUNet:
     """Weights of one UNet (or ControlNet trunk) repacked for the kernels, resident in HBM as fp16."""
 
@@ -157,8 +168,9 @@ class PackedUNet:
             As, rows = [], []
             r_off = 0
             r_tot = sum(0 if ab is None else ab[0].shape[0] for ab in parts["ab"])
+            dev0 = next(ab[0].device for ab in parts["ab"] if ab is not None)
             for ab, n_rows in zip(parts["ab"], parts["rows"]):
-                blk = torch.zeros(n_rows, r_tot)
+                blk = torch.zeros(n_rows, r_tot, device=dev0)
                 if ab is not None:
                     A, Bm = ab
                     As.append(A)
@@ -216,6 +228,7 @@ class UNetRunner:
         self.ws: Dict[str, torch.Tensor] = {}
         self.use_graphs = use_graphs
         self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.graph_launches: Dict[tuple, int] = {}
         self.warm: set = set()
         self.temb_table = None
         self.kv: Dict[str, torch.Tensor] = {}
@@ -228,7 +241,7 @@ class UNetRunner:
         self.cross_weights: List[float] = []
         self.cond_emb = None
         self.residuals_in = None   # (9 skip residual tensors, mid residual, scale) produced by a ControlNet runner
-        self.stats_ws = torch.empty(batch * 64, dtype=torch.float32, device=self.dev)
+        self.stats_ws = torch.empty(batch * 64 * 257, dtype=torch.float32, device=self.dev)
 
     # ------------------------------------------------------------------------------------------- buffers
     def buf(self, name, shape) -> torch.Tensor:
@@ -465,6 +478,7 @@ class UNetRunner:
             return fn(variant)
         if key in self.graphs:
             self.graphs[key].replay()
+            REPLAYED_LAUNCHES[0] += self.graph_launches[key]
             return self._out[key]
         if key not in self.warm:
             self.warm.add(key)
@@ -473,8 +487,12 @@ class UNetRunner:
             return self._out[key]
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
+        n0 = L.launch_count()
         with torch.cuda.graph(g):
             self._out[key] = fn(variant)
+        self.graph_launches[key] = L.launch_count() - n0
+        CAPTURED_LAUNCHES[0] += self.graph_launches[key]
         self.graphs[key] = g
         g.replay()
+        REPLAYED_LAUNCHES[0] += self.graph_launches[key]
         return self._out[key]
