@@ -1,0 +1,164 @@
+"""CPU tests: the C-ABI library loads and exports every declared symbol, host-side logic (prompt-to-prompt tables,
+schedule, masks, config arithmetic, LoRA packing) and the 2-rank gloo path of the data-parallel plumbing."""
+import ctypes
+import math
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+from make_golden import ToyTokenizer  # noqa: E402
+
+
+def test_library_exports_every_declared_symbol():
+    from omg_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "omg_b200.h")).read()
+    declared = set(re.findall(r"\b(omg_[a-z0-9_]+)\s*\(", hdr))
+    declared = {d for d in declared if not d.endswith("_desc")}
+    assert {"omg_gemm", "omg_attention", "omg_groupnorm", "omg_layernorm", "omg_fuse_step", "omg_ctx_mix", "omg_axpy",
+            "omg_last_error", "omg_version", "omg_launch_count"} <= declared
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} not exported"
+    assert set(_lib.SYMBOLS) == declared
+    l2 = _lib.load()
+    assert l2.omg_version().decode().startswith("omg_b200")
+    assert l2.omg_launch_count() == 0
+
+
+def test_struct_sizes_match_c_layout():
+    """ctypes mirrors of the descriptors must have the C sizes (checked against a compile-time table)."""
+    from omg_b200 import _lib
+    assert ctypes.sizeof(_lib.View4) == 48
+    assert ctypes.sizeof(_lib.Seg) == 28
+    assert ctypes.sizeof(_lib.GemmDesc) % 8 == 0
+    assert ctypes.sizeof(_lib.AttnDesc) % 8 == 0
+
+
+def test_no_cpu_fallback():
+    from omg_b200 import ops
+    with pytest.raises(ValueError):
+        ops.linear(torch.zeros(8, 8), torch.zeros(8, 8))
+
+
+def test_p2p_tables_match_reference_golden():
+    from omg_b200.prompt_attention import AttentionReplace
+    G = os.path.join(ROOT, "tests", "golden")
+    d = torch.load(os.path.join(G, "p2p_same.pt"))
+    c = AttentionReplace(d["prompts"], 50, {"default_": 1.0}, 0.4, 4, 4, tokenizer=ToyTokenizer())
+    assert torch.equal(c.cross_replace_alpha, d["alpha"]) and torch.equal(c.mapper, d["mapper"])
+    assert c.num_self_replace == (0, 20)
+    d = torch.load(os.path.join(G, "p2p_edit.pt"))
+    c = AttentionReplace(d["prompts"], d["num_steps"], dict(d["cross"]), d["self"], 4, 4, tokenizer=ToyTokenizer())
+    assert torch.equal(c.cross_replace_alpha, d["alpha"]) and torch.equal(c.mapper, d["mapper"])
+    with pytest.raises(ValueError):
+        AttentionReplace(["a b c", "a b"], 10, 1.0, 0.4, 4, 4, tokenizer=ToyTokenizer())
+
+
+def test_p2p_counters_and_edit_spec():
+    from omg_b200.prompt_attention import AttentionReplace
+    c = AttentionReplace(["x y"] * 2, 50, {"default_": 1.0}, 0.4, 32, 32)
+    c.num_att_layers = 140
+    assert c.self_replace_active(1024) and not c.self_replace_active(4096)
+    c.advance(139)
+    assert (c.cur_step, c.cur_att_layer) == (0, 139)
+    c.advance(1)
+    assert (c.cur_step, c.cur_att_layer) == (1, 0)
+    c.advance(140 * 19)
+    assert c.cur_step == 20 and not c.self_replace_active(1024)
+    base, keep = c.cross_edit()
+    assert torch.equal(base, torch.eye(77)) and keep is None
+    c.reset()
+    assert (c.cur_step, c.cur_att_layer) == (0, 0)
+    with pytest.raises(RuntimeError):
+        c(torch.zeros(4, 2, 2), True, "mid")
+    c.cur_step = 51
+    with pytest.raises(IndexError):
+        c.cross_edit()
+
+
+def test_cross_edit_equals_probability_edit():
+    """P0 (M diag(a) V) + P1 (diag(1-a) V) == ((P0 M) * a + (1-a) * P1) V for the reference's edit."""
+    from omg_b200.prompt_attention import AttentionReplace
+    c = AttentionReplace(["a photo of a man", "a photo of a dog"], 10, {"default_": 0.6, "dog": (0.2, 0.9)}, 0.3, 4, 4,
+                         tokenizer=ToyTokenizer())
+    g = torch.Generator().manual_seed(0)
+    for step in (0, 2, 7, 9):
+        c.cur_step = step
+        base, keep = c.cross_edit()
+        P0 = torch.softmax(torch.randn(5, 77, generator=g), -1)
+        P1 = torch.softmax(torch.randn(5, 77, generator=g), -1)
+        V = torch.randn(77, 16, generator=g)
+        alpha = c.cross_replace_alpha[step, 0, 0, 0]
+        ref = ((P0 @ c.mapper[0]) * alpha + (1 - alpha) * P1) @ V
+        mine = P0 @ (base @ V) + (P1 @ (keep @ V) if keep is not None else 0)
+        assert torch.allclose(mine, ref, atol=1e-5)
+
+
+def test_schedule_matches_published_sdxl_values():
+    from omg_b200.scheduler import EulerDiscreteSchedule
+    s = EulerDiscreteSchedule()
+    ts = s.set_timesteps(30)
+    assert ts[0] == 958.0 and ts[-1] == 1.0 and s.sigmas[-1] == 0.0
+    sig_max = math.sqrt((1 - s.alphas_cumprod[-1]) / s.alphas_cumprod[-1])
+    assert abs(sig_max - 14.6146) < 1e-3
+    assert abs(s.init_noise_sigma - math.sqrt(s.sigmas[0] ** 2 + 1)) < 1e-6
+    assert np.all(np.diff(s.sigmas) < 0)
+
+
+def test_config_arithmetic():
+    from omg_b200.config import UNetConfig, lora_target_names, param_shapes, unet_flops
+    cfg = UNetConfig.sdxl()
+    assert sum(math.prod(v) for v in param_shapes(cfg).values()) == 2_567_463_684
+    assert abs(unet_flops(cfg, 128, 128) / 1e12 - 6.761) < 2e-3
+    assert len(lora_target_names(cfg)) == 722
+
+
+def test_latent_mask_is_nearest_and_binary():
+    from omg_b200.pipelines import _binary_latent_mask
+    m = torch.zeros(64, 64)
+    m[8:24, 16:40] = 1
+    m[40, 40] = 0.5
+    out = _binary_latent_mask(m, 8, 8, "cpu").reshape(8, 8)
+    ref = (torch.nn.functional.interpolate(m[None, None], size=(8, 8), mode="nearest")[0, 0] == 1).float()
+    assert torch.equal(out, ref) and out.sum() == 6
+    assert _binary_latent_mask(None, 8, 8, "cpu") is None
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from omg_b200.distributed import broadcast_state_dict, gather_latents, shard_indices
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sd = {"b": torch.full((3,), float(rank)), "a": torch.arange(4.0) * (rank + 1)}
+    broadcast_state_dict(sd, 0)
+    n = 5
+    idx = shard_indices(n, rank, world)
+    local = torch.stack([torch.full((2, 2), float(j)) for j in idx])
+    allv = gather_latents(local, n)
+    q.put((rank, sd["a"].tolist(), sd["b"].tolist(), allv[:, 0, 0].tolist(), idx))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_plumbing_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    for rank, a, b, allv, idx in res:
+        assert a == [0.0, 1.0, 2.0, 3.0] and b == [0.0, 0.0, 0.0]      # rank 0's weights everywhere
+        assert allv == [0.0, 1.0, 2.0, 3.0, 4.0]                       # image order restored
+    assert res[0][4] == [0, 2, 4] and res[1][4] == [1, 3]
