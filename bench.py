@@ -110,6 +110,17 @@ def cpu_sample_forward_seconds(cfg, sd_cpu, latent, threads, reps=1):
     return best
 
 
+def host_threads():
+    """Threads for the CPU arm: the cores this process may run on, capped at 32 (measured on the GPU box: torch's
+    intra-op pool gets slower beyond 32 threads on the 128-core host; 32 threads: 2.3 s, 64 threads: 5.8 s for the same
+    64x64-latent sample-forward)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(32, n))
+
+
 def cpu_state_dict(cfg, device):
     from omg_b200 import synthetic
     if torch.cuda.is_available():
@@ -126,7 +137,7 @@ def run_reference(args, rank, world):
         return
     from omg_b200.config import UNetConfig
     cfg = UNetConfig.sdxl()
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     sd = cpu_state_dict(cfg, "cuda:0" if torch.cuda.is_available() else "cpu")
     latent = IMAGE // 8
     for _ in range(args.warmup):
@@ -317,7 +328,7 @@ def main():
             torch.cuda.synchronize()
             out["unet_step_ms"]["main_b4"] = e0.elapsed_time(e1) / 5
         if not args.no_cpu_baseline and world == 1:
-            threads = os.cpu_count() or 1
+            threads = host_threads()
             sd_cpu = cpu_state_dict(cfg, dev)
             t = cpu_sample_forward_seconds(cfg, sd_cpu, IMAGE // 8, threads)
             out["cpu_baseline"] = {"value": 1.0 / (SAMPLE_FORWARDS_PER_IMAGE * t), "unit": "images/sec",

@@ -10,9 +10,14 @@
 //     cross-attention edit  P_0 (M diag(a) V_1) + P_1 (diag(1-a) V_1).
 //
 // CTA = one (item, head, 256-query slab): two 128-row Q tiles ping-pong through one MMA issuer so the tensor core
-// works on one tile while the other tile's softmax runs.  320 threads: warp 0 TMA, warp 1 tcgen05.mma issuer,
-// warps 2-5 / 6-9 softmax groups (one query row per thread; TMEM lane == row, so no shuffles are needed).
-// TMEM: S0 | S1 (128 cols each, fp32 scores) | O[group][2] (64 cols each, per-KV-block P.V partials).
+// works on one tile while the other tile's softmax runs.  384 threads = 3 warpgroups: warp 0 TMA, warp 1 tcgen05.mma
+// issuer (setmaxnreg gives their registers away), warps 4-7 / 8-11 softmax groups (one query row per thread: TMEM
+// lane == row, so no shuffles are needed; 224 registers each hold a whole 128-key score row).
+// TMEM: S0 | S1 (128 cols each, fp32 scores) | O0 | O1 (64 cols each, the running P.V accumulator of each tile).
+// Softmax follows the lazy-rescale scheme: O stays in TMEM and is accumulated by the tensor core across KV blocks;
+// the running maximum is allowed to go stale by up to 2^8 and O is only rescaled (TMEM load-scale-store) when a row
+// maximum grows beyond that, which after the first blocks is rare.  exp2 runs on the MUFU for 3 of 4 elements and as
+// a degree-3 polynomial on the FMA pipe for the 4th (the MUFU is the bottleneck unit at head_dim 64).
 #include <cuda_fp16.h>
 #include <math.h>
 #include <string.h>
@@ -23,7 +28,7 @@
 
 namespace omg {
 
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 384;  // warpgroup 0: TMA + MMA warps (+2 idle), warpgroups 1,2: softmax groups
 constexpr int ATT_BQ = 128;   // rows per softmax group
 constexpr int ATT_BKV = 128;  // keys per block
 constexpr int ATT_D = 64;
@@ -60,9 +65,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
     uint64_t* s_full = kv_empty + ATT_KV_STAGES;  // 2
     uint64_t* p_full = s_full + 2;                // 2
     uint64_t* p_empty = p_full + 2;               // 2
-    uint64_t* o_full = p_empty + 2;               // 2 x 2  [g*2 + buf]
-    uint64_t* o_empty = o_full + 4;               // 2 x 2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 4);
+    uint64_t* o_full = p_empty + 2;               // 2: P.V of the current block has completed (O_g, P_g reusable)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -84,10 +88,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
             mbar_init(&s_full[g], 1);
             mbar_init(&p_full[g], 4);
             mbar_init(&p_empty[g], 1);
-            for (int b = 0; b < 2; ++b) {
-                mbar_init(&o_full[g * 2 + b], 1);
-                mbar_init(&o_empty[g * 2 + b], 4);
-            }
+            mbar_init(&o_full[g], 1);
         }
         fence_barrier_init();
     }
@@ -96,8 +97,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // TMEM columns: S_g at g*128, O_g[buf] at 256 + g*128 + buf*64
-    if (warp == 0) {
+    // TMEM columns: S_g at g*128, O_g at 256 + g*64
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+      if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             mbar_arrive_expect_tx(q_full, 2 * ATT_Q_BYTES);
@@ -146,22 +149,20 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
                     nstage = 0;
                     nphase ^= 1;
                 }
-                const int ob = j & 1;
                 for (int g = 0; g < 2; ++g) {
                     mbar_wait(&p_full[g], j & 1);
-                    mbar_wait(&o_empty[g * 2 + ob], ((j >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t p_addr = smem_u32(p_smem + g * ATT_P_BYTES);
                     const uint32_t v_addr = smem_u32(kv_smem + stage * 2 * ATT_KV_BYTES + ATT_KV_BYTES);
-                    const uint32_t d_tmem = tmem_base + 256 + g * 128 + ob * 64;
+                    const uint32_t d_tmem = tmem_base + 256 + g * 64;
 #pragma unroll
                     for (int k = 0; k < ATT_BKV / 16; ++k) {
                         // A = P: K-major, two 64-wide (16 KB) halves; B = V: 16 key rows (2 KB) per K step
                         const uint64_t a = umma_desc_sw128(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 1024, 16);
                         const uint64_t b = umma_desc_sw128(v_addr + k * 2048, 1024, 1024);
-                        tc_mma_f16_ss(d_tmem, a, b, idesc_o, k > 0);
+                        tc_mma_f16_ss(d_tmem, a, b, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
                     }
-                    tc_commit(&o_full[g * 2 + ob]);
+                    tc_commit(&o_full[g]);
                     tc_commit(&p_empty[g]);
                     if (j + 1 < nkv) {
                         mbar_wait(&kv_full[nstage], nphase);
@@ -174,80 +175,78 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
                 phase = nphase;
             }
         }
+      }
     } else {
         // ------------------------------------------------------------------ softmax groups
-        const int g = (warp - 2) >> 2;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        const int g = (warp - 4) >> 2;
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t s_tmem = tmem_base + g * 128 + lane_base;
         uint8_t* my_p = p_smem + g * ATT_P_BYTES;
-        float m = -INFINITY, l = 0.f, corr_prev = 0.f;
-        float o_acc[ATT_D];
-#pragma unroll
-        for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.f;
-
-        auto accumulate_o = [&](int jb, float corr) {
-            const int ob = jb & 1;
-            mbar_wait(&o_full[g * 2 + ob], (jb >> 1) & 1);
-            tc_fence_after();
-            const uint32_t o_tmem = tmem_base + 256 + g * 128 + ob * 64 + lane_base;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(o_tmem + c * 32, r);
-                tc_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * corr + __uint_as_float(r[i]);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&o_empty[g * 2 + ob]);
-        };
+        const uint32_t o_tmem = tmem_base + 256 + g * 64 + lane_base;
+        float m = -INFINITY, l = 0.f;
+        constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P may reach 2^8 before O is rescaled
 
         for (int j = 0; j < nkv; ++j) {
             mbar_wait(&s_full[g], j & 1);
             tc_fence_after();
             const int kv_left = p.n_kv - j * ATT_BKV;  // valid keys in this block (>= 1)
-            // pass 1: row maximum
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(s_tmem + c * 32, r);
-                tc_wait_ld();
-                if (kv_left >= (c + 1) * 32) {
+            uint32_t sr[4][32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-                } else {
+            for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_tmem + c * 32, sr[c]);
+            tc_wait_ld();
+            if (kv_left < ATT_BKV) {  // partial last block: keys beyond n_kv (zero-filled K rows) are excluded
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i < kv_left) mx = fmaxf(mx, __uint_as_float(r[i]));
+                        if (c * 32 + i >= kv_left) sr[c][i] = __float_as_uint(-INFINITY);
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
+            const float m_cand = fmaxf(m, mx * p.scale_log2);
+            if (j == 0) {
+                m = m_cand;
+            } else {
+                const bool need = (m_cand - m) > kRescaleThreshold;
+                if (__any_sync(0xffffffffu, need)) {
+                    // O_g holds blocks < j relative to the stale maximum: rescale it once P.V(j-1) has landed
+                    mbar_wait(&o_full[g], (j - 1) & 1);
+                    tc_fence_after();
+                    const float corr = need ? fast_exp2(m - m_cand) : 1.0f;
+                    if (need) m = m_cand;
+                    l *= corr;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(o_tmem + c * 32, r);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+                        tmem_st_32x32(o_tmem + c * 32, r);
+                    }
+                    tc_wait_st();
                 }
             }
-            const float m_new = fmaxf(m, mx * p.scale_log2);
-            const float corr = fast_exp2(m - m_new);  // m == -inf on the first block -> 0
-            m = m_new;
-            // P buffer must have been consumed by the previous block's P.V
+            // the P buffer must have been consumed by the previous block's P.V
             mbar_wait(&p_empty[g], (j & 1) ^ 1);
             float sum = 0.f;
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < 4; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(s_tmem + c * 32, r);
-                tc_wait_ld();
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    float p0 = fast_exp2(__uint_as_float(r[2 * i]) * p.scale_log2 - m_new);
-                    float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * p.scale_log2 - m_new);
-                    if (c * 32 + 2 * i >= kv_left) p0 = 0.f;
-                    if (c * 32 + 2 * i + 1 >= kv_left) p1 = 0.f;
-                    // the row sum uses the fp16-rounded probabilities the tensor core will consume
-                    const __half2 h = __floats2half2_rn(p0, p1);
-                    const float2 f = __half22float2(h);
-                    sum += f.x + f.y;
-                    pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+                    const float x0 = fmaf(__uint_as_float(sr[c][2 * i]), p.scale_log2, -m);
+                    const float x1 = fmaf(__uint_as_float(sr[c][2 * i + 1]), p.scale_log2, -m);
+                    const float p0 = fast_exp2(x0);
+                    const float p1 = (i & 1) ? poly_exp2(x1) : fast_exp2(x1);
+                    sum += p0 + p1;
+                    pk[i] = pack_half2(p0, p1);
                 }
                 // K-major SWIZZLE_128B: half hh = c >> 1, 16 B chunk index within the 128 B row = (c & 1) * 4 + t
                 uint8_t* rowp = my_p + (c >> 1) * 16384 + row * 128;
@@ -258,15 +257,24 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
                         make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
                 }
             }
-            l = l * corr + sum;
+            l += sum;
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[g]);
-            if (j > 0) accumulate_o(j - 1, corr_prev);
-            corr_prev = corr;
         }
-        accumulate_o(nkv - 1, corr_prev);
+        // all P.V of this tile have landed
+        mbar_wait(&o_full[g], (nkv - 1) & 1);
+        tc_fence_after();
+        float o_acc[ATT_D];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(o_tmem + c * 32, r);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = __uint_as_float(r[i]);
+        }
 
         // finalise: out = (accumulate ? out : 0) + w * O / l
         const int qrow = slab * 256 + g * 128 + row;

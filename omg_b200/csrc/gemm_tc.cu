@@ -346,20 +346,19 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
 
 static int pick_block_n(int N, int epilogue, long m_tiles) {
     if (epilogue == OMG_EPI_GEGLU) return 256;
-    // prefer exact division (no wasted columns), then fewer/larger tiles while keeping >= ~1.5 waves of work
+    // time ~ waves * per-tile cost.  Per-tile costs are empirical (kernel_bench on B200, profiles/): narrow tiles
+    // re-read the A tile from shared memory once per BN columns, so cost per column rises as BN shrinks.
     const int cands[4] = {256, 160, 128, 64};
-    int best = 64;
-    double best_cost = 1e30;
-    for (int c : cands) {
-        const long nt = (N + c - 1) / c;
-        const long tiles = nt * m_tiles;
-        const long waves = (tiles + 147) / 148;
-        // cost ~ waves * per-tile time; small tiles are smem-bandwidth-bound (A tile re-read per 64 columns)
-        const double per_tile = (double)c + 64.0 * (c < 128 ? 1.0 : 0.25);
-        const double cost = (double)waves * per_tile;
-        if (cost < best_cost - 1e-9) {
-            best_cost = cost;
-            best = c;
+    const double cost[4] = {256.0, 200.0, 175.0, 110.0};
+    int best = 256;
+    double best_t = 1e30;
+    for (int i = 0; i < 4; ++i) {
+        const long nt = (N + cands[i] - 1) / cands[i];
+        const long waves = (nt * m_tiles + 147) / 148;
+        const double t = (double)waves * cost[i];
+        if (t < best_t - 1e-9) {
+            best_t = t;
+            best = cands[i];
         }
     }
     return best;

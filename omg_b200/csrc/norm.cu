@@ -38,8 +38,7 @@ __global__ void gn_partial_kernel(GnSrc s, int HW, int cpg, int rows_per_cta, fl
     float a[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = q[i] = 0.f;
-    for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-        const uint4 u = gn_load8(s, (size_t)b * HW + r, c);
+    auto acc8 = [&](const uint4& u) {
         const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -49,7 +48,20 @@ __global__ void gn_partial_kernel(GnSrc s, int HW, int cpg, int rows_per_cta, fl
             a[2 * i + 1] += f.y;
             q[2 * i + 1] += f.y * f.y;
         }
+    };
+    int r = r0 + threadIdx.y;
+    const int step = blockDim.y;
+    for (; r + 3 * step < r1; r += 4 * step) {  // four independent 16 B loads in flight per thread
+        const uint4 u0 = gn_load8(s, (size_t)b * HW + r, c);
+        const uint4 u1 = gn_load8(s, (size_t)b * HW + r + step, c);
+        const uint4 u2 = gn_load8(s, (size_t)b * HW + r + 2 * step, c);
+        const uint4 u3 = gn_load8(s, (size_t)b * HW + r + 3 * step, c);
+        acc8(u0);
+        acc8(u1);
+        acc8(u2);
+        acc8(u3);
     }
+    for (; r < r1; r += step) acc8(gn_load8(s, (size_t)b * HW + r, c));
     float* s_sum = s_red;
     float* s_sq = s_red + blockDim.y * C;
 #pragma unroll
@@ -86,56 +98,82 @@ __global__ void gn_partial_kernel(GnSrc s, int HW, int cpg, int rows_per_cta, fl
 
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int splits, float inv_n, float eps,
                                    float* __restrict__ stats) {
-    const int b = blockIdx.x, g = threadIdx.x;
+    const int b = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;  // block = 32 groups x 32 lanes
     float sa = 0.f, sq = 0.f;
-    for (int k = 0; k < splits; ++k) {
-        const float* p = partial + (((size_t)b * splits + k) * 32 + g) * 2;
-        sa += p[0];
-        sq += p[1];
+    for (int k = lane; k < splits; k += 32) {
+        const float2 p = *reinterpret_cast<const float2*>(partial + (((size_t)b * splits + k) * 32 + g) * 2);
+        sa += p.x;
+        sq += p.y;
     }
-    const float mean = sa * inv_n;
-    const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
-    stats[((size_t)b * 32 + g) * 2] = mean;
-    stats[((size_t)b * 32 + g) * 2 + 1] = rsqrtf(var + eps);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {  // fixed-order tree: deterministic
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (lane == 0) {
+        const float mean = sa * inv_n;
+        const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
+        stats[((size_t)b * 32 + g) * 2] = mean;
+        stats[((size_t)b * 32 + g) * 2 + 1] = rsqrtf(var + eps);
+    }
 }
 
-// grid = (ceil(HW*C/8 / 256), B)
+// grid = (ceil(HW*C/8 / (256*2)), B): two 16 B vectors per thread (same channel offset, rows r and r + half)
 __global__ void gn_apply_kernel(GnSrc s, int HW, int cpg, int silu, const float* __restrict__ stats,
                                 const __half* __restrict__ gamma, const __half* __restrict__ beta,
                                 __half* __restrict__ y) {
     const int C = s.C1 + s.C2;
     const int vec_per_row = C / 8;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (size_t)HW * vec_per_row) return;
     const int b = blockIdx.y;
-    const size_t r = idx / vec_per_row;
-    const int c = (int)(idx % vec_per_row) * 8;
-    const uint4 u = gn_load8(s, (size_t)b * HW + r, c);
-    const uint4 gw = *reinterpret_cast<const uint4*>(gamma + c);
-    const uint4 bw = *reinterpret_cast<const uint4*>(beta + c);
-    const __half* xh = reinterpret_cast<const __half*>(&u);
-    const __half* gh = reinterpret_cast<const __half*>(&gw);
-    const __half* bh = reinterpret_cast<const __half*>(&bw);
-    float out[8];
-    int g_cur = -1;
-    float mean = 0.f, rstd = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int g = (c + i) / cpg;
-        if (g != g_cur) {
-            g_cur = g;
-            mean = stats[((size_t)b * 32 + g) * 2];
-            rstd = stats[((size_t)b * 32 + g) * 2 + 1];
+    const size_t total = (size_t)HW * vec_per_row;
+    const size_t idx0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (idx0 >= total) return;
+    // consecutive vectors of one thread: same row unless the row ends (vec_per_row is even for C % 16 == 0)
+    size_t r = idx0 / vec_per_row;
+    int c = (int)(idx0 - r * vec_per_row) * 8;
+    const int n_vec = (idx0 + 1 < total) ? 2 : 1;
+    uint4 u[2];
+    size_t rr[2];
+    int cc[2];
+    for (int v = 0; v < n_vec; ++v) {
+        rr[v] = r;
+        cc[v] = c;
+        u[v] = gn_load8(s, (size_t)b * HW + r, c);
+        c += 8;
+        if (c >= C) {
+            c = 0;
+            ++r;
         }
-        float v = (__half2float(xh[i]) - mean) * rstd * __half2float(gh[i]) + __half2float(bh[i]);
-        if (silu) v = v / (1.0f + __expf(-v));
-        out[i] = v;
     }
-    uint4 o;
-    __half2* oh = reinterpret_cast<__half2*>(&o);
+    for (int v = 0; v < n_vec; ++v) {
+        const int c0 = cc[v];
+        const uint4 gw = *reinterpret_cast<const uint4*>(gamma + c0);
+        const uint4 bw = *reinterpret_cast<const uint4*>(beta + c0);
+        const __half* xh = reinterpret_cast<const __half*>(&u[v]);
+        const __half* gh = reinterpret_cast<const __half*>(&gw);
+        const __half* bh = reinterpret_cast<const __half*>(&bw);
+        int g = c0 / cpg;
+        int rem = c0 - g * cpg;
+        float mean = stats[((size_t)b * 32 + g) * 2], rstd = stats[((size_t)b * 32 + g) * 2 + 1];
+        float out[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(out[2 * i], out[2 * i + 1]);
-    *reinterpret_cast<uint4*>(y + ((size_t)b * HW + r) * C + c) = o;
+        for (int i = 0; i < 8; ++i) {
+            float val = (__half2float(xh[i]) - mean) * rstd * __half2float(gh[i]) + __half2float(bh[i]);
+            if (silu) val = val / (1.0f + __expf(-val));
+            out[i] = val;
+            if (++rem == cpg && i < 7) {
+                rem = 0;
+                ++g;
+                mean = stats[((size_t)b * 32 + g) * 2];
+                rstd = stats[((size_t)b * 32 + g) * 2 + 1];
+            }
+        }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(out[2 * i], out[2 * i + 1]);
+        *reinterpret_cast<uint4*>(y + ((size_t)b * HW + rr[v]) * C + c0) = o;
+    }
 }
 
 // One warp per token row; exact two-pass variance held in registers (C <= 2560).
@@ -225,7 +263,7 @@ extern "C" int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int
     if (ty > 16) ty = 16;
     if (ty < 1) ty = 1;
     // enough CTAs to fill the machine: ~4 per SM across the batch, at most OMG_GN_MAX_SPLITS per image
-    int splits = (148 * 4 + B - 1) / B;
+    int splits = (148 * 2 + B - 1) / B;
     if (splits > OMG_GN_MAX_SPLITS) splits = OMG_GN_MAX_SPLITS;
     int rows_per_cta = (HW + splits - 1) / splits;
     if (rows_per_cta < ty) rows_per_cta = ty;
@@ -240,10 +278,10 @@ extern "C" int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int
     }
     gn_partial_kernel<<<dim3(splits, B), dim3(tx, ty), smem, stream>>>(s, HW, cpg, rows_per_cta, partial);
     if (check_launch("gn_partial_kernel")) return 1;
-    gn_finalize_kernel<<<B, 32, 0, stream>>>(partial, splits, 1.0f / ((float)HW * (float)cpg), eps, stats);
+    gn_finalize_kernel<<<B, 1024, 0, stream>>>(partial, splits, 1.0f / ((float)HW * (float)cpg), eps, stats);
     if (check_launch("gn_finalize_kernel")) return 1;
     const size_t nvec = (size_t)HW * (C / 8);
-    gn_apply_kernel<<<dim3((unsigned)((nvec + 255) / 256), B), 256, 0, stream>>>(
+    gn_apply_kernel<<<dim3((unsigned)((nvec + 511) / 512), B), 256, 0, stream>>>(
         s, HW, cpg, silu, stats, static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
         static_cast<__half*>(y));
     return check_launch("gn_apply_kernel");
