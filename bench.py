@@ -203,7 +203,9 @@ def main():
             dist.broadcast(sd[k], src=0)
         torch.cuda.synchronize()
     t_bcast = time.perf_counter() - t_b0
-    wl = factory.build_lora_workload(cfg, IMAGE, 2, 32, STEPS_PER_STAGE, 7.5, device=dev, state_dict=sd)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):  # keep stdout to the single JSON line
+        wl = factory.build_lora_workload(cfg, IMAGE, 2, 32, STEPS_PER_STAGE, 7.5, device=dev, state_dict=sd)
     del sd
     pipe = wl.pipe
     kw = dict(wl.call_kwargs)

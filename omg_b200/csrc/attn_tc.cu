@@ -150,8 +150,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
                     nphase ^= 1;
                 }
                 for (int g = 0; g < 2; ++g) {
-                    mbar_wait(&p_full[g], j & 1);
+                    mbar_wait(&p_full[g], j & 1);  // P_g(j) is in smem and S_g has been read out
                     tc_fence_after();
+                    // S_g(j+1) first: it is what the softmax group waits for next; P.V(j) only has to land before
+                    // the next block's probabilities overwrite the P buffer
+                    if (j + 1 < nkv) {
+                        mbar_wait(&kv_full[nstage], nphase);
+                        tc_fence_after();
+                        issue_s(g, nstage);
+                    }
                     const uint32_t p_addr = smem_u32(p_smem + g * ATT_P_BYTES);
                     const uint32_t v_addr = smem_u32(kv_smem + stage * 2 * ATT_KV_BYTES + ATT_KV_BYTES);
                     const uint32_t d_tmem = tmem_base + 256 + g * 64;
@@ -164,11 +171,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
                     }
                     tc_commit(&o_full[g]);
                     tc_commit(&p_empty[g]);
-                    if (j + 1 < nkv) {
-                        mbar_wait(&kv_full[nstage], nphase);
-                        tc_fence_after();
-                        issue_s(g, nstage);
-                    }
                 }
                 tc_commit(&kv_empty[stage]);
                 stage = nstage;
@@ -184,7 +186,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t s_tmem = tmem_base + g * 128 + lane_base;
-        uint8_t* my_p = p_smem + g * ATT_P_BYTES;
+        // this row's 16 B chunk slots inside a 128 B swizzled row: slot(t) = (t ^ (row & 7)) * 16
+        const uint32_t my_p = smem_u32(p_smem + g * ATT_P_BYTES) + row * 128;
+        const uint32_t sw = (uint32_t)(row & 7) << 4;
         const uint32_t o_tmem = tmem_base + 256 + g * 64 + lane_base;
         float m = -INFINITY, l = 0.f;
         constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P may reach 2^8 before O is rescaled
@@ -249,13 +253,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
                     pk[i] = pack_half2(p0, p1);
                 }
                 // K-major SWIZZLE_128B: half hh = c >> 1, 16 B chunk index within the 128 B row = (c & 1) * 4 + t
-                uint8_t* rowp = my_p + (c >> 1) * 16384 + row * 128;
+                const uint32_t rowp = my_p + (c >> 1) * 16384;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int chunk = ((c & 1) * 4 + t) ^ (row & 7);
-                    *reinterpret_cast<uint4*>(rowp + chunk * 16) =
-                        make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-                }
+                for (int t = 0; t < 4; ++t)
+                    st_shared_v4(rowp + ((((c & 1) * 4 + t) << 4) ^ sw), pk[4 * t], pk[4 * t + 1], pk[4 * t + 2],
+                                 pk[4 * t + 3]);
             }
             l += sum;
             fence_proxy_async_smem();

@@ -211,12 +211,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             // pixel origin of this warp's 32-row store box
             const int sh = h0 + (q * 32) / p.tw, sw = w0 + (q * 32) % p.tw;
 
+            // residual rows are fetched two chunks ahead (the first two before the accumulator is even ready), so
+            // their HBM/L2 latency hides behind the mainloop / the previous chunks instead of stalling each chunk
+            constexpr int NCH = BN / ACC_PER_CHUNK;
+            uint4 res[2][4];
+            const bool has_res = (EPI != OMG_EPI_GEGLU) && p.residual != nullptr && row_valid;
+            const __half* res_row = has_res ? p.residual + pix * (size_t)p.residual_ld + n0 : nullptr;
+            auto load_res = [&](int c, uint4(&dst)[4]) {
+                if (has_res && n0 + c * 32 < p.N) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(res_row + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dst[j] = __ldg(rp + j);
+                }
+            };
+            if constexpr (EPI != OMG_EPI_GEGLU) {
+                load_res(0, res[0]);
+                if (NCH > 1) load_res(1, res[1]);
+            }
+
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
 
-#pragma unroll 1
-            for (int c = 0; c < BN / ACC_PER_CHUNK; ++c) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
                 const int nacc0 = n0 + c * ACC_PER_CHUNK;
                 if (nacc0 >= p.N) break;
                 uint32_t outp[16];
@@ -262,12 +280,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
                     }
-                    if (p.residual != nullptr && row_valid) {
-                        const uint4* rp =
-                            reinterpret_cast<const uint4*>(p.residual + pix * (size_t)p.residual_ld + nacc0);
+                    if (has_res) {
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
-                            const uint4 u = __ldg(rp + j4);
+                            const uint4 u = res[c & 1][j4];
                             const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
@@ -276,6 +292,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                                 v[j4 * 8 + 2 * t + 1] += f.y;
                             }
                         }
+                        if (c + 2 < NCH) load_res(c + 2, res[c & 1]);
                     }
 #pragma unroll
                     for (int j = 0; j < 16; ++j) outp[j] = pack_half2(v[2 * j], v[2 * j + 1]);
