@@ -262,12 +262,16 @@ extern "C" int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int
     int ty = 1024 / tx;
     if (ty > 16) ty = 16;
     if (ty < 1) ty = 1;
-    // enough CTAs to fill the machine: ~4 per SM across the batch, at most OMG_GN_MAX_SPLITS per image
-    int splits = (148 * 2 + B - 1) / B;
-    if (splits > OMG_GN_MAX_SPLITS) splits = OMG_GN_MAX_SPLITS;
-    int rows_per_cta = (HW + splits - 1) / splits;
-    if (rows_per_cta < ty) rows_per_cta = ty;
-    splits = (HW + rows_per_cta - 1) / rows_per_cta;
+    // the row partition depends on (HW, C) only - never on the batch size - so an image's statistics are
+    // bit-identical whatever batch it is processed in (grouped multi-stream forwards rely on this)
+    int rows_per_cta = (HW + 63) / 64;
+    if (rows_per_cta < 4 * ty) rows_per_cta = 4 * ty;
+    int splits = (HW + rows_per_cta - 1) / rows_per_cta;
+    if (splits > OMG_GN_MAX_SPLITS) {
+        splits = OMG_GN_MAX_SPLITS;
+        rows_per_cta = (HW + splits - 1) / splits;
+        splits = (HW + rows_per_cta - 1) / rows_per_cta;
+    }
     float* stats = static_cast<float*>(stats_ws);             // [B][32][2] mean, rstd
     float* partial = stats + (size_t)B * 64;                  // [B][splits][32][2]
     const size_t smem = (size_t)2 * ty * C * sizeof(float);

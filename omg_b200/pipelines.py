@@ -127,6 +127,7 @@ class _BasePipeline:
         self.scheduler = EulerDiscreteSchedule()
         self.use_graphs = use_graphs
         self.controller: Optional[AttentionReplace] = None
+        self.main_lora_key: Optional[str] = None
         self._runners: Dict[tuple, UNetRunner] = {}
         self.timings: Dict[str, float] = {}
 
@@ -135,13 +136,19 @@ class _BasePipeline:
         return self.unet.device
 
     # ---------------------------------------------------------------------------------------------- helpers
-    def _runner(self, tag, model: PackedUNet, batch, h, w, lora_key=None) -> UNetRunner:
-        key = (tag, id(model), batch, h, w, lora_key)
+    def _runner(self, tag, model: PackedUNet, batch, h, w, lora_key=None, groups=None, tag_extra=None) -> UNetRunner:
+        key = (tag, id(model), batch, h, w, lora_key, tag_extra)
         r = self._runners.get(key)
         if r is None:
-            r = UNetRunner(model, batch, h, w, lora_key=lora_key, use_graphs=self.use_graphs)
+            r = UNetRunner(model, batch, h, w, lora_key=lora_key, use_graphs=self.use_graphs, groups=groups)
             self._runners[key] = r
         return r
+
+    def load_lora_weights(self, lora: dict, adapter_name: str = "style", scale: float = 0.8, **_):
+        """Style LoRA on the main UNet (inference_lora.py:163; applied with cross_attention_kwargs scale 0.8)."""
+        key = f"main:{adapter_name}@{scale:g}"
+        self.unet.add_lora_set(key, [(lora, 1.0)], scale)
+        self.main_lora_key = key
 
     def encode_prompt(self, prompt, negative_prompt, lora_scale=None):
         """-> prompt_embeds (n,77,D), negative (n,77,D), pooled (n,P), negative pooled (n,P) for a list of prompts."""
@@ -183,14 +190,16 @@ class _BasePipeline:
             v["cross_weights"].append(1.0)
         return v, key + (True, v["self_replace"], two)
 
-    def _update_p2p_context(self, runner: UNetRunner, controller: AttentionReplace, ctx4: torch.Tensor, first: bool):
+    def _update_p2p_context(self, runners, controller: AttentionReplace, ctx4: torch.Tensor, first: bool):
         """(Re)build the mixed context rows 4,5 when the step's alpha row differs from the previous step's."""
+        if isinstance(runners, UNetRunner):
+            runners = [runners]
         coef_base, coef_keep = controller.cross_edit()
         sig = (coef_base.numpy().tobytes(), None if coef_keep is None else coef_keep.numpy().tobytes())
         if not first and sig == self._p2p_sig:
             return
         self._p2p_sig = sig
-        dev = runner.dev
+        dev = self._execution_device
         c1 = ctx4[3:4].to(dev, torch.float16).contiguous()
         mix_a = ops.ctx_mix(c1, coef_base.to(dev).contiguous())
         if coef_keep is not None:
@@ -202,7 +211,135 @@ class _BasePipeline:
         if first:
             self._p2p_rows = rows
         else:
-            runner.update_context_rows(4, rows)
+            for r in runners:
+                r.update_context_rows(4, rows)
+
+    def _denoise(self, *, ts, lat, ctx4, pooled4, tid, concepts, masks, stage, guidance_scale, h, w, concept_unet,
+                 main_cn=None, identity=None):
+        """The step loop (lora_pipeline.py:485-632 / instantid_pipeline.py:540-690).
+
+        concepts: list of dicts {ctx (2, L, D) [text tokens (+ IP tokens)], pooled (2, P), lora_key, ip (bool)};
+        main_cn:  None or (ControlNet PackedUNet, condition image (4,3,H,W), scale, keep(i) -> 0/1) for the main rows;
+        identity: None or (IdentityNet PackedUNet, condition image (2,3,H,W), scale, [face tokens (2,16,D) per concept]).
+
+        Steps without fusion run the main UNet alone (B=4).  Fusion steps (index > 15, stage 2) run ONE grouped
+        forward: rows 0-3 = main stream, then two rows per active concept, every stream with its own LoRA segment /
+        IP term / IdentityNet residuals - when the concept UNet shares the packed base weights with the main UNet
+        (the reference's two pipelines load the same checkpoint, inference_lora.py:153-159); otherwise the concept
+        streams run as separate forwards."""
+        dev = self._execution_device
+        sig = self.scheduler.sigmas
+        controller = self.controller
+        active = [k for k in range(len(concepts)) if stage == 2 and masks[k] is not None]
+        n_act = len(active)
+        grouped = n_act > 0 and concept_unet is self.unet
+        from .unet import RowGroup
+        main = self._runner("main", self.unet, 4, h, w, groups=[RowGroup(0, 4, self.main_lora_key, False)])
+        extra = None
+        if controller is not None:
+            self._update_p2p_context([], controller, ctx4, first=True)
+            extra = self._p2p_rows
+        main.set_conditioning(ts, ctx4, pooled4, tid.repeat(4, 1), extra_ctx=extra)
+        p2p_runners = [main]
+        fused, crun = None, []
+        if grouped:
+            groups = [RowGroup(0, 4, self.main_lora_key, False)]
+            ctx_list = [(ctx4, self.main_lora_key, False)]
+            for j, k in enumerate(active):
+                c = concepts[k]
+                groups.append(RowGroup(4 + 2 * j, 6 + 2 * j, c["lora_key"], c["ip"]))
+                ctx_list.append((c["ctx"], c["lora_key"], c["ip"]))
+            fused = self._runner("fused", self.unet, 4 + 2 * n_act, h, w, groups=groups,
+                                 tag_extra=tuple((g.lora_key, g.ip) for g in groups))
+            fused.set_conditioning(ts, ctx_list, torch.cat([pooled4.to(dev)] + [concepts[k]["pooled"].to(dev) for k in active]),
+                                   tid.repeat(4 + 2 * n_act, 1), extra_ctx=extra)
+            p2p_runners.append(fused)
+        else:
+            for k in active:
+                c = concepts[k]
+                r = self._runner(f"concept{k}", concept_unet, 2, h, w,
+                                 groups=[RowGroup(0, 2, c["lora_key"], c["ip"])], tag_extra=(c["lora_key"], c["ip"]))
+                r.set_conditioning(ts, c["ctx"], c["pooled"], tid.repeat(2, 1))
+                crun.append(r)
+        cn = None
+        if main_cn is not None:
+            cn_model, cn_cond, cn_scale, cn_keep = main_cn
+            cn = self._runner("cn", cn_model, 4, h, w, groups=[RowGroup(0, 4, None, False)])
+            cn.set_conditioning(ts, ctx4, pooled4, tid.repeat(4, 1))
+            cn.set_controlnet_cond(cn_cond)
+        idr = None
+        if identity is not None and n_act > 0:
+            id_model, id_cond, id_scale, id_tokens = identity
+            idr = self._runner("identity", id_model, 2 * n_act, h, w, groups=[RowGroup(0, 2 * n_act, None, False)])
+            idr.set_conditioning(ts, torch.cat([id_tokens[k].to(dev) for k in active]),
+                                 torch.cat([concepts[k]["pooled"].to(dev) for k in active]), tid.repeat(2 * n_act, 1))
+            idr.set_controlnet_cond(id_cond.repeat(n_act, 1, 1, 1))
+        # initial model inputs: scale_model_input(cat([latents]*2), t0)  (:491-492)
+        x0 = (lat * self.scheduler.input_scale(0)).half()
+        main.sample_in[..., :4] = torch.cat([x0, x0], dim=0)
+        cbuf = torch.zeros((2, h, w, 8), dtype=torch.float16, device=dev)  # scaled image-1 latent twice (:583-585)
+        cbuf[..., :4] = torch.cat([x0[1:2], x0[1:2]], dim=0)
+        lat = lat.contiguous()
+        n_att = self.unet.num_attention_layers()
+        for i in range(len(ts)):
+            fuse = i > FUSION_AFTER_STEP and n_act > 0
+            if controller is not None:
+                self._update_p2p_context(p2p_runners, controller, ctx4, first=False)
+            run = fused if (fuse and grouped) else main
+            variant, key = self._p2p_variant(run, controller, cn is not None)
+            if run is fused:
+                run.sample_in[0:4].copy_(main.sample_in)
+                for j in range(n_act):
+                    run.sample_in[4 + 2 * j:6 + 2 * j].copy_(cbuf)
+                # concept streams: plain attention on their own K/V rows (after the main 4 text rows + 2 P2P rows)
+                kv0 = 4 + (2 if controller is not None else 0)
+                ident_c = [(4 + r, 4 + r, kv0 + r, kv0 + r) for r in range(2 * n_act)]
+                variant["self_items"] = variant["self_items"][:4] + [(4 + r, 4 + r, 4 + r, 4 + r) for r in range(2 * n_act)]
+                variant["cross_items"] = [variant["cross_items"][0][:4] + ident_c] + variant["cross_items"][1:]
+                variant["ip_items"], n_ip = [], 0
+                for j, k in enumerate(active):
+                    if concepts[k]["ip"]:
+                        for r in (4 + 2 * j, 5 + 2 * j):
+                            variant["ip_items"].append((r, r, n_ip, n_ip))
+                            n_ip += 1
+            if cn is not None:
+                cn.sample_in.copy_(main.sample_in)
+                down, mid = cn.forward(i, key=("cn",))
+                sc = cn_scale * cn_keep(i)
+                run.residuals_in = (down, mid, sc, 0)
+                key = key + (sc,)
+            if fuse and idr is not None:
+                for j in range(n_act):
+                    idr.sample_in[2 * j:2 * j + 2].copy_(cbuf)
+                down, mid = idr.forward(i, key=("identity",))
+            if run is fused and idr is not None:
+                # IdentityNet residuals go to the concept rows only; a main-row ControlNet would need a second slot
+                if cn is not None:
+                    raise NotImplementedError("main-pass ControlNet together with IdentityNet in one grouped forward")
+                run.residuals_in = (down, mid, id_scale, 4)
+                variant["residuals"] = True
+                key = key + ("id", id_scale)
+            noise = run.forward(i, variant, key=key)
+            if controller is not None:
+                controller.advance(n_att)
+            noises, fmasks = [], []
+            if fuse:
+                if grouped:
+                    noises = [noise[4 + 2 * j:6 + 2 * j] for j in range(n_act)]
+                else:
+                    for j, r in enumerate(crun):
+                        r.sample_in.copy_(cbuf)
+                        v = r.default_variant()
+                        ckey = ("concept",)
+                        if idr is not None:
+                            r.residuals_in = ([d[2 * j:2 * j + 2] for d in down], mid[2 * j:2 * j + 2], id_scale, 0)
+                            v["residuals"] = True
+                            ckey = ("concept", "id", id_scale)
+                        noises.append(r.forward(i, v, key=ckey))
+                fmasks = [masks[k] for k in active]
+            ops.fuse_step(noise[0:4] if run is fused else noise, noises, fmasks, guidance_scale, float(sig[i]),
+                          float(sig[i + 1]), lat, main.sample_in, cbuf)
+        return lat
 
     def _finish(self, latents_nhwc: torch.Tensor, output_type: str, return_dict: bool):
         lat = latents_nhwc.permute(0, 3, 1, 2).contiguous().half()  # (2,4,h,w) like the reference's fp16 latents
@@ -266,66 +403,21 @@ class LoraMultiConceptPipeline(_BasePipeline):
         tid = torch.tensor([list(original_size) + list(crops_coords_top_left) + list(target_size)], dtype=torch.float32)
         ctx4 = torch.cat([negative_prompt_embeds, prompt_embeds], dim=0)          # rows [neg0, neg1, pos0, pos1]
         pooled4 = torch.cat([negative_pooled_prompt_embeds, pooled_prompt_embeds], dim=0)
-        # runners
-        controller = self.controller  # installed by revise_regionally_controlnet_forward; the kwarg is ignored (:248)
-        main = self._runner("main", self.unet, 4, h, w)
-        extra = None
-        if controller is not None:
-            self._update_p2p_context(main, controller, ctx4, first=True)
-            extra = self._p2p_rows
-        main.set_conditioning(ts, ctx4, pooled4, tid.repeat(4, 1), extra_ctx=extra)
-        cn = None
-        use_cn = image is not None and self.controlnet is not None
-        if use_cn:
-            cn = self._runner("cn", self.controlnet, 4, h, w)
-            cn.set_conditioning(ts, ctx4, pooled4, tid.repeat(4, 1))
-            cn.set_controlnet_cond(self._prepare_image(image, width, height, 4))
-        crun = []
-        for k, c in enumerate(concepts):
-            if stage == 2 and masks[k] is not None:
-                r = self._runner(f"concept{k}", concept_models.unet, 2, h, w, lora_key=c["lora_key"])
-                r.set_conditioning(ts, c["ctx"], c["pooled"], tid.repeat(2, 1))
-                crun.append(r)
-            else:
-                crun.append(None)
-        cn_scale = controlnet_conditioning_scale[0] if isinstance(controlnet_conditioning_scale, list) else controlnet_conditioning_scale
-        # initial model inputs: scale_model_input(cat([latents]*2), t0)  (:491-492)
-        x0 = (lat * self.scheduler.input_scale(0)).half()
-        main.sample_in[..., :4] = torch.cat([x0, x0], dim=0)
-        for r in crun:
-            if r is not None:
-                r.sample_in[..., :4] = torch.cat([x0[1:2], x0[1:2]], dim=0)
-        if cn is not None:
-            cn.sample_in.copy_(main.sample_in)
-        lat = lat.contiguous()
-        n_att = self.unet.num_attention_layers()
-        for i in range(len(ts)):
-            if controller is not None:
-                self._update_p2p_context(main, controller, ctx4, first=False)
-            variant, key = self._p2p_variant(main, controller, use_cn)
-            if cn is not None:
-                keep = 1.0 - float(i / len(ts) < control_guidance_start or (i + 1) / len(ts) > control_guidance_end)
-                down, mid = cn.forward(i, key=("cn",))
-                main.residuals_in = (down, mid, cn_scale * keep)
-                key = key + (cn_scale * keep,)  # the scale is baked into the captured launch
-            noise = main.forward(i, variant, key=key)
-            if controller is not None:
-                controller.advance(n_att)
-            fuse = i > FUSION_AFTER_STEP and stage == 2
-            cn_noise = []
-            if fuse:
-                for r in crun:
-                    cn_noise.append(None if r is None else r.forward(i, key=("concept",)))
-            ops.fuse_step(noise, cn_noise if fuse else [], masks if fuse else [], guidance_scale, float(sig[i]),
-                          float(sig[i + 1]), lat, main.sample_in,
-                          next((r.sample_in for r in crun if r is not None), None))
-            # all concept runners read the same input (latent_model_input[3:4] twice, :583-585)
-            first = next((r for r in crun if r is not None), None)
-            for r in crun:
-                if r is not None and r is not first:
-                    r.sample_in.copy_(first.sample_in)
-            if cn is not None:
-                cn.sample_in.copy_(main.sample_in)
+        # the controller acts through self.controller (installed by revise_regionally_controlnet_forward); the
+        # `controller=` kwarg is accepted and ignored exactly like the reference (:248)
+        main_cn = None
+        if image is not None and self.controlnet is not None:
+            cn_scale = controlnet_conditioning_scale[0] if isinstance(controlnet_conditioning_scale, list) else controlnet_conditioning_scale
+            n_ts = len(ts)
+            s0 = control_guidance_start[0] if isinstance(control_guidance_start, list) else control_guidance_start
+            e0 = control_guidance_end[0] if isinstance(control_guidance_end, list) else control_guidance_end
+            main_cn = (self.controlnet, self._prepare_image(image, width, height, 4), cn_scale,
+                       lambda i: 1.0 - float(i / n_ts < s0 or (i + 1) / n_ts > e0))      # controlnet_keep (:421-427)
+        for c in concepts:
+            c["ip"] = False
+        lat = self._denoise(ts=ts, lat=lat, ctx4=ctx4, pooled4=pooled4, tid=tid, concepts=concepts, masks=masks,
+                            stage=stage, guidance_scale=guidance_scale, h=h, w=w, concept_unet=concept_models.unet
+                            if concept_models is not None else self.unet, main_cn=main_cn)
         return self._finish(lat, output_type, return_dict)
 
     def _prepare_image(self, image, width, height, batch):
@@ -401,79 +493,24 @@ class InstantidMultiConceptPipeline(_BasePipeline):
         tid = torch.tensor([list(original_size) + list(crops_coords_top_left) + list(target_size)], dtype=torch.float32)
         ctx4 = torch.cat([negative_prompt_embeds, prompt_embeds], dim=0)
         pooled4 = torch.cat([negative_pooled_prompt_embeds, pooled_prompt_embeds], dim=0)
-        controller = self.controller
-        main = self._runner("main", self.unet, 4, h, w)
-        extra = None
-        if controller is not None:
-            self._update_p2p_context(main, controller, ctx4, first=True)
-            extra = self._p2p_rows
-        main.set_conditioning(ts, ctx4, pooled4, tid.repeat(4, 1), extra_ctx=extra)
-        cn2 = None
+        main_cn = None
         if t2i_image is not None and self.controlnet2 is not None:
-            cn2 = self._runner("cn2", self.controlnet2, 4, h, w)
-            cn2.set_conditioning(ts, ctx4, pooled4, tid.repeat(4, 1))
-            cn2.set_controlnet_cond(LoraMultiConceptPipeline._prepare_image(self, t2i_image, width, height, 4))
-        crun, idrun = [], []
-        use_id = image is not None and self.controlnet is not None
-        for k, c in enumerate(concepts):
-            if stage == 2 and masks[k] is not None:
-                r = self._runner(f"concept{k}", concept_models.unet, 2, h, w)
-                r.set_conditioning(ts, torch.cat([c["ctx"].to(dev), c["tokens"].to(dev)], dim=1), c["pooled"],
-                                   tid.repeat(2, 1))
-                crun.append(r)
-                if use_id:
-                    ir = self._runner(f"identity{k}", self.controlnet, 2, h, w)
-                    ir.set_conditioning(ts, c["tokens"], c["pooled"], tid.repeat(2, 1))
-                    ir.set_controlnet_cond(LoraMultiConceptPipeline._prepare_image(self, image, width, height, 2))
-                    idrun.append(ir)
-                else:
-                    idrun.append(None)
-            else:
-                crun.append(None)
-                idrun.append(None)
+            t2i_scale = t2i_controlnet_conditioning_scale[0] if isinstance(t2i_controlnet_conditioning_scale, list) else t2i_controlnet_conditioning_scale
+            main_cn = (self.controlnet2, LoraMultiConceptPipeline._prepare_image(self, t2i_image, width, height, 4),
+                       t2i_scale, lambda i: 1.0)
+        identity = None
         cn_scale = controlnet_conditioning_scale[0] if isinstance(controlnet_conditioning_scale, list) else controlnet_conditioning_scale
-        t2i_scale = t2i_controlnet_conditioning_scale[0] if isinstance(t2i_controlnet_conditioning_scale, list) else t2i_controlnet_conditioning_scale
-        x0 = (lat * self.scheduler.input_scale(0)).half()
-        main.sample_in[..., :4] = torch.cat([x0, x0], dim=0)
-        for r in crun + idrun:
-            if r is not None:
-                r.sample_in[..., :4] = torch.cat([x0[1:2], x0[1:2]], dim=0)
-        if cn2 is not None:
-            cn2.sample_in.copy_(main.sample_in)
-        lat = lat.contiguous()
-        n_att = self.unet.num_attention_layers()
-        for i in range(len(ts)):
-            if controller is not None:
-                self._update_p2p_context(main, controller, ctx4, first=False)
-            variant, key = self._p2p_variant(main, controller, cn2 is not None)
-            if cn2 is not None:
-                down, mid = cn2.forward(i, key=("cn2",))
-                main.residuals_in = (down, mid, t2i_scale)
-                key = key + (t2i_scale,)
-            noise = main.forward(i, variant, key=key)
-            if controller is not None:
-                controller.advance(n_att)
-            fuse = i > FUSION_AFTER_STEP and stage == 2
-            cn_noise = []
-            if fuse:
-                for r, ir in zip(crun, idrun):
-                    if r is None:
-                        cn_noise.append(None)
-                        continue
-                    v = r.default_variant()
-                    if ir is not None:
-                        down, mid = ir.forward(i, key=("identity",))
-                        r.residuals_in = (down, mid, cn_scale)
-                        v["residuals"] = True
-                    cn_noise.append(r.forward(i, v, key=("concept", ir is not None, cn_scale)))
-            first = next((r for r in crun if r is not None), None)
-            ops.fuse_step(noise, cn_noise if fuse else [], masks if fuse else [], guidance_scale, float(sig[i]),
-                          float(sig[i + 1]), lat, main.sample_in, None if first is None else first.sample_in)
-            for r in crun + idrun:
-                if r is not None and r is not first:
-                    r.sample_in.copy_(first.sample_in)
-            if cn2 is not None:
-                cn2.sample_in.copy_(main.sample_in)
+        for c in concepts:
+            c["lora_key"] = None
+            c["ip"] = c["tokens"] is not None
+            if c["ip"]:
+                c["ctx"] = torch.cat([c["ctx"].to(dev), c["tokens"].to(dev).to(c["ctx"].dtype)], dim=1)  # (:663)
+        if stage == 2 and image is not None and self.controlnet is not None:
+            identity = (self.controlnet, LoraMultiConceptPipeline._prepare_image(self, image, width, height, 2), cn_scale,
+                        [c["tokens"] for c in concepts])
+        lat = self._denoise(ts=ts, lat=lat, ctx4=ctx4, pooled4=pooled4, tid=tid, concepts=concepts, masks=masks,
+                            stage=stage, guidance_scale=guidance_scale, h=h, w=w, concept_unet=concept_models.unet
+                            if concept_models is not None else self.unet, main_cn=main_cn, identity=identity)
         return self._finish(lat, output_type, return_dict)
 
     def get_face_embedding(self, face_app, ref_image):

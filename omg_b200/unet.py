@@ -216,14 +216,26 @@ class PackedUNet:
         return 2 * sum(layers for _, _, layers in self.tr_names)
 
 
+class RowGroup:
+    """A contiguous range of batch rows that shares one adapter configuration ("stream").  Several streams - the
+    main UNet rows and every concept's rows - run through ONE launch sequence: the base weights are shared, each
+    stream contributes its own LoRA K-segment (its block of t = A x is non-zero only on its rows), its own IP-adapter
+    attention term and its own ControlNet residuals.  This is the parity-exact form of "one kernel computes every
+    concept" (SURVEY section 7, step 8)."""
+
+    def __init__(self, start: int, stop: int, lora_key: Optional[str] = None, ip: bool = False):
+        self.start, self.stop, self.lora_key, self.ip = start, stop, lora_key, ip
+
+
 class UNetRunner:
     """One (model, batch, latent size) execution context: preallocated activations, hoisted per-call tables,
     CUDA graphs per variant."""
 
     def __init__(self, model: PackedUNet, batch: int, H: int, W: int, lora_key: Optional[str] = None,
-                 use_graphs: bool = True):
+                 use_graphs: bool = True, groups: Optional[List[RowGroup]] = None):
         self.m, self.B, self.H, self.W = model, batch, H, W
-        self.lora = model.lora_sets[lora_key] if lora_key else {}
+        self.groups = groups or [RowGroup(0, batch, lora_key, model.ip is not None)]
+        self._b2_cache: Dict[str, torch.Tensor] = {}
         self.dev = model.device
         self.ws: Dict[str, torch.Tensor] = {}
         self.use_graphs = use_graphs
@@ -240,7 +252,9 @@ class UNetRunner:
         self.cross_items: List[List[tuple]] = []
         self.cross_weights: List[float] = []
         self.cond_emb = None
-        self.residuals_in = None   # (9 skip residual tensors, mid residual, scale) produced by a ControlNet runner
+        # (9 skip residual tensors, mid residual, scale[, row0]) produced by a ControlNet runner; added to the batch
+        # rows [row0, row0 + residual batch)
+        self.residuals_in = None
         self.stats_ws = torch.empty(batch * 64 * 257, dtype=torch.float32, device=self.dev)
 
     # ------------------------------------------------------------------------------------------- buffers
@@ -251,20 +265,48 @@ class UNetRunner:
             self.ws[name] = t
         return t
 
-    def _lin(self, key, x2d, out, bias=None, residual=None, epilogue=L.EPI_NONE):
+    def zbuf(self, name, shape) -> torch.Tensor:
+        t = self.ws.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.zeros(shape, dtype=torch.float16, device=self.dev)
+            self.ws[name] = t
+        return t
+
+    def _lin(self, key, x2d, out, bias=None, residual=None, epilogue=L.EPI_NONE, groups=None, rows_per_item=None):
+        """Linear with the un-merged LoRA deltas of every row group: t[rows_g, cols_g] = x[rows_g] A_g^T (skinny
+        GEMMs, the other blocks of t stay zero), then ONE GEMM over all rows whose extra K-segment is t against
+        [s B_1 | s B_2 | ...]."""
         P = self.m.p
-        lo = self.lora.get(key)
-        if lo is None:
+        groups = self.groups if groups is None else groups
+        active = [(g, self.m.lora_sets[g.lora_key][key]) for g in groups
+                  if g.lora_key and key in self.m.lora_sets[g.lora_key]]
+        if not active:
             return ops.linear(x2d, P[key + ".w"], bias=bias, residual=residual, out=out, epilogue=epilogue)
-        A_cat, B2 = lo
-        t = ops.linear(x2d, A_cat, out=self.buf(f"lora_t.{A_cat.shape[0]}.{x2d.shape[0]}", (x2d.shape[0], A_cat.shape[0])))
-        return ops.linear(x2d, P[key + ".w"], bias=bias, residual=residual, out=out, epilogue=epilogue, lora=(t, B2))
+        M = x2d.shape[0]
+        n = rows_per_item if rows_per_item is not None else M // (groups[-1].stop - groups[0].start)
+        r_tot = sum(a.shape[0] for _, (a, _) in active)
+        sig = ",".join(f"{g.start}-{g.stop}:{a.shape[0]}" for g, (a, _) in active)
+        t = self.zbuf(f"lora_t.{M}.{sig}", (M, r_tot))
+        ck = key + "|" + sig + "|" + ",".join(g.lora_key for g, _ in active)
+        b2 = self._b2_cache.get(ck)
+        if b2 is None:
+            b2 = torch.cat([bm for _, (_, bm) in active], dim=1).contiguous() if len(active) > 1 else active[0][1][1]
+            self._b2_cache[ck] = b2
+        c0 = 0
+        base = groups[0].start
+        for g, (a_cat, _) in active:
+            r0, r1 = (g.start - base) * n, (g.stop - base) * n
+            ops.linear(x2d[r0:r1], a_cat, out=t[r0:r1, c0:c0 + a_cat.shape[0]])
+            c0 += a_cat.shape[0]
+        return ops.linear(x2d, P[key + ".w"], bias=bias, residual=residual, out=out, epilogue=epilogue, lora=(t, b2))
 
     # ------------------------------------------------------------------------------------------- per-call setup
-    def set_conditioning(self, timesteps, ctx: torch.Tensor, text_embeds: torch.Tensor, time_ids: torch.Tensor,
+    def set_conditioning(self, timesteps, ctx, text_embeds: torch.Tensor, time_ids: torch.Tensor,
                          extra_ctx: Optional[torch.Tensor] = None):
-        """Hoisted, step-invariant work (see module docstring).  ctx (B, L, D) [text tokens, then IP tokens if the
-        model has an IP adapter]; extra_ctx: further context rows appended for prompt-to-prompt mixed contexts."""
+        """Hoisted, step-invariant work (see module docstring).  text_embeds / time_ids: one row per batch row.
+        ctx: (rows, L, D) [text tokens, then IP tokens for IP streams], or a list of (ctx, lora_key, has_ip) segments
+        (one per stream; K/V rows are numbered in list order); extra_ctx: further text rows of the FIRST segment
+        (prompt-to-prompt mixed contexts)."""
         m, cfg, P, B = self.m, self.m.cfg, self.m.p, self.B
         dev = self.dev
         ts = torch.as_tensor(timesteps, dtype=torch.float32, device=dev).reshape(-1)
@@ -281,40 +323,55 @@ class UNetRunner:
         self.temb_table = ops.linear(act, P["temb_all.w"], bias=P["temb_all.b"]).reshape(T, B, m.temb_cols)
         self.set_context(ctx, extra_ctx)
 
-    def set_context(self, ctx: torch.Tensor, extra_ctx: Optional[torch.Tensor] = None):
-        """Project the cross-attention K/V of every attn2 layer once (text rows [+ mixed rows]; IP tokens)."""
-        m, P = self.m, self.m.p
-        ctx = ctx.to(self.dev, torch.float16)
-        n_ip = m.ip_tokens if m.ip is not None else 0
-        txt = ctx[:, : ctx.shape[1] - n_ip].contiguous()
-        if extra_ctx is not None:
-            txt = torch.cat([txt, extra_ctx.to(self.dev, torch.float16)], dim=0).contiguous()
-        self.ctx_txt = txt
+    def set_context(self, ctx, extra_ctx: Optional[torch.Tensor] = None):
+        """Project the cross-attention K/V of every attn2 layer once per call (they are step-invariant): text rows
+        of every stream with that stream's LoRA [+ mixed rows]; IP-adapter image tokens of the IP streams."""
+        m = self.m
+        if torch.is_tensor(ctx):
+            g0 = self.groups[0]
+            ctx = [(ctx, g0.lora_key, g0.ip)]
+        txts, segs, ips = [], [], []
+        row = 0
+        for i, (c, lora_key, has_ip) in enumerate(ctx):
+            c = c.to(self.dev, torch.float16)
+            n_ip = m.ip_tokens if has_ip else 0
+            t = c[:, : c.shape[1] - n_ip]
+            if i == 0 and extra_ctx is not None:
+                t = torch.cat([t, extra_ctx.to(self.dev, torch.float16)], dim=0)
+            txts.append(t)
+            segs.append(RowGroup(row, row + t.shape[0], lora_key))
+            if n_ip:
+                ips.append(c[:, c.shape[1] - n_ip:])
+            row += t.shape[0]
+        txt = torch.cat(txts, dim=0).contiguous()
+        self.ctx_txt, self.ctx_segs = txt, segs
         self.ctx_rows, self.ctx_len = txt.shape[0], txt.shape[1]
         txt2d = txt.reshape(-1, txt.shape[-1])
-        ip2d = ctx[:, ctx.shape[1] - n_ip:].contiguous().reshape(-1, ctx.shape[-1]) if n_ip else None
+        ip = torch.cat(ips, dim=0).contiguous() if ips else None
         for name, ch, layers in m.tr_names:
             for k in range(layers):
                 b = f"{name}.transformer_blocks.{k}"
                 kv = self.buf(b + ".kv", (self.ctx_rows, self.ctx_len, 2 * ch))
-                self._lin(b + ".attn2.kv", txt2d, kv.view(-1, 2 * ch))
+                self._lin(b + ".attn2.kv", txt2d, kv.view(-1, 2 * ch), groups=segs, rows_per_item=self.ctx_len)
                 self.kv[b] = kv
-                if n_ip:
-                    kvi = self.buf(b + ".kv_ip", (ctx.shape[0], n_ip, 2 * ch))
-                    ops.linear(ip2d, m.ip[b + ".attn2"], out=kvi.view(-1, 2 * ch))
+                if ip is not None:
+                    kvi = self.buf(b + ".kv_ip", (ip.shape[0], ip.shape[1], 2 * ch))
+                    ops.linear(ip.reshape(-1, ip.shape[-1]), m.ip[b + ".attn2"], out=kvi.view(-1, 2 * ch))
                     self.kv_ip[b] = kvi
 
     def update_context_rows(self, row0: int, rows: torch.Tensor):
-        """Re-project K/V for context rows [row0, row0+n) only (prompt-to-prompt mixed contexts that change with the
-        step's alpha)."""
+        """Re-project K/V for the text context rows [row0, row0+n) of the first segment only (prompt-to-prompt mixed
+        contexts that change with the step's alpha)."""
         m = self.m
         n = rows.shape[0]
         self.ctx_txt[row0:row0 + n].copy_(rows)
         x2d = self.ctx_txt[row0:row0 + n].reshape(-1, rows.shape[-1])
+        seg = [RowGroup(0, n, self.ctx_segs[0].lora_key)]
         for name, ch, layers in m.tr_names:
             for k in range(layers):
                 b = f"{name}.transformer_blocks.{k}"
-                self._lin(b + ".attn2.kv", x2d, self.kv[b][row0:row0 + n].view(-1, 2 * ch))
+                self._lin(b + ".attn2.kv", x2d, self.kv[b][row0:row0 + n].view(-1, 2 * ch), groups=seg,
+                          rows_per_item=self.ctx_len)
 
     def set_controlnet_cond(self, cond: torch.Tensor):
         """ControlNet conditioning embedding of the (constant) condition image (B,3,Himg,Wimg) in [0,1]: conv stack
@@ -383,9 +440,9 @@ class UNetRunner:
             for ti, (items, wgt) in enumerate(zip(variant["cross_items"], variant["cross_weights"])):
                 ops.attention(q, kv, kv, o, heads, N, self.ctx_len, items, 0, 0, ch, scale=scale, out_weight=wgt,
                               accumulate=ti > 0)
-            if m.ip is not None:
+            if variant.get("ip_items"):
                 kvi = self.kv_ip[b]
-                ops.attention(q, kvi, kvi, o, heads, N, m.ip_tokens, ident, 0, 0, ch, scale=scale,
+                ops.attention(q, kvi, kvi, o, heads, N, m.ip_tokens, variant["ip_items"], 0, 0, ch, scale=scale,
                               out_weight=m.ip_scale, accumulate=True)
             self._lin(b + ".attn2.out", o.view(M, ch), h, bias=P[b + ".attn2.out.b"], residual=h)
             ops.layernorm(h, P[b + ".norm3.g"], P[b + ".norm3.b"], out=ln)
@@ -424,10 +481,12 @@ class UNetRunner:
                         out=self.buf("conv_in.out", (B, H, W, cfg.block_out_channels[0])))
         h, skips = self._encoder(h, variant)
         if variant.get("residuals", False):
-            down_r, mid_r, r_scale = self.residuals_in  # ControlNet outputs * conditioning_scale
-            skips = [ops.axpy(s, r, r_scale, out=self.buf(f"skip_add.{i}", tuple(s.shape))) for i, (s, r) in
-                     enumerate(zip(skips, down_r))]
-            h = ops.axpy(h, mid_r, r_scale, out=self.buf("mid_add", tuple(h.shape)))
+            # ControlNet outputs * conditioning_scale, added in place to the rows of the stream they belong to
+            down_r, mid_r, r_scale = self.residuals_in[:3]
+            r0 = self.residuals_in[3] if len(self.residuals_in) > 3 else 0
+            for sk, r in zip(skips + [h], list(down_r) + [mid_r]):
+                dst = sk[r0:r0 + r.shape[0]]
+                ops.axpy(dst, r, r_scale, out=dst)
         nb = len(cfg.block_out_channels)
         for i in range(nb):
             ch, layers = cfg.block_out_channels[nb - 1 - i], cfg.transformer_layers[nb - 1 - i]
@@ -464,9 +523,17 @@ class UNetRunner:
 
     # ------------------------------------------------------------------------------------------- public
     def default_variant(self) -> dict:
+        """Identity attention routing: K/V row == batch row; IP term for the rows of IP streams (IP K/V rows are
+        numbered in stream order)."""
         ident = [(b, b, b, b) for b in range(self.B)]
+        ip_items, n = [], 0
+        for g in self.groups:
+            if g.ip:
+                for b in range(g.start, g.stop):
+                    ip_items.append((b, b, n, n))
+                    n += 1
         return {"self_replace": False, "self_threshold": 0, "self_items": ident, "cross_items": [ident],
-                "cross_weights": [1.0], "residuals": False}
+                "cross_weights": [1.0], "residuals": False, "ip_items": ip_items}
 
     def forward(self, step_index: int, variant: Optional[dict] = None, key: Optional[tuple] = None):
         """Run one forward for the timestep `step_index` of the schedule given to set_conditioning.  The input is

@@ -22,7 +22,10 @@ def _masks(size):
     return m1, m2
 
 
-def test_lora_two_stage_pipeline():
+@pytest.mark.parametrize("share", [False, True])
+def test_lora_two_stage_pipeline(share):
+    """share=True: the concept UNet is the main UNet's packed weights -> fusion steps run as ONE grouped forward
+    (main rows + both concepts' rows); share=False: separate concept forwards."""
     from omg_b200.config import UNetConfig
     from omg_b200.pipelines import ConceptModels, LoraMultiConceptPipeline, revise_regionally_controlnet_forward
     from omg_b200.prompt_attention import AttentionReplace
@@ -39,7 +42,7 @@ def test_lora_two_stage_pipeline():
     pipe = LoraMultiConceptPipeline(PackedUNet(cfg, sd))
     controller = AttentionReplace(prompts, 50, {"default_": 1.0}, 0.4, width=8, height=8)
     revise_regionally_controlnet_forward(pipe, controller)
-    cm = ConceptModels(PackedUNet(cfg, sd))
+    cm = ConceptModels(pipe.unet if share else PackedUNet(cfg, sd))
     loras = [lora(cfg, 101), lora(cfg, 102)]
     cm.load_lora_weights(loras[0], adapter_name="manA")
     cm.load_lora_weights(loras[1], adapter_name="womanB")
@@ -55,7 +58,10 @@ def test_lora_two_stage_pipeline():
     controller.reset()
     out2 = pipe(stage=2, region_masks=masks, **common).images
     assert torch.equal(out1[0], out1[1])                      # stage 1: both rows identical trajectories
-    assert torch.equal(out2[0], out1[0])                      # image 0 of stage 2 reproduces the layout image
+    if share:   # grouped B=8 launches may tile differently from B=4: equal up to fp16 rounding noise
+        assert rel(out2[0], out1[0]) < 2e-3
+    else:
+        assert torch.equal(out2[0], out1[0])                  # image 0 of stage 2 reproduces the layout image
     assert not torch.equal(out2[1], out2[0])
 
     # ---- oracle
@@ -112,7 +118,8 @@ def test_lora_pipeline_skips_concept_without_mask_and_style_adapter():
     assert e < 2e-2
 
 
-def test_instantid_two_stage_pipeline():
+@pytest.mark.parametrize("share", [False, True])
+def test_instantid_two_stage_pipeline(share):
     from omg_b200 import synthetic
     from omg_b200.config import UNetConfig
     from omg_b200.pipelines import ConceptModels, InstantidMultiConceptPipeline, revise_regionally_controlnet_forward
@@ -132,7 +139,7 @@ def test_instantid_two_stage_pipeline():
     prompts = ["two people"] * 2
     controller = AttentionReplace(prompts, 50, {"default_": 1.0}, 0.4, width=4, height=4)
     revise_regionally_controlnet_forward(pipe, controller)
-    cm = ConceptModels(PackedUNet(cfg, sd))
+    cm = ConceptModels(pipe.unet if share else PackedUNet(cfg, sd))
     cm.load_ip_adapter_instantid(rs["sd"], ipw, heads=rs["heads"], dim_head=rs["dim_head"], num_tokens=16)
     cm.set_ip_adapter_scale(0.8)
     g = torch.Generator().manual_seed(53)
