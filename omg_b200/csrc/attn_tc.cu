@@ -13,7 +13,8 @@
 // works on one tile while the other tile's softmax runs.  384 threads = 3 warpgroups: warp 0 TMA, warp 1 tcgen05.mma
 // issuer (setmaxnreg gives their registers away), warps 4-7 / 8-11 softmax groups (one query row per thread: TMEM
 // lane == row, so no shuffles are needed; 224 registers each hold a whole 128-key score row).
-// TMEM: S0 | S1 (128 cols each, fp32 scores) | O0 | O1 (64 cols each, the running P.V accumulator of each tile).
+// KV blocks are 64 keys; TMEM: S_g[2] (2 x 64 cols of fp32 scores per tile, double-buffered) | O0 | O1 (64 cols each,
+// the running P.V accumulator of each tile).
 // Softmax follows the lazy-rescale scheme: O stays in TMEM and is accumulated by the tensor core across KV blocks;
 // the running maximum is allowed to go stale by up to 2^8 and O is only rescaled (TMEM load-scale-store) when a row
 // maximum grows beyond that, which after the first blocks is rare.  exp2 runs on the MUFU for 3 of 4 elements and as
@@ -29,17 +30,17 @@
 namespace omg {
 
 constexpr int ATT_THREADS = 384;  // warpgroup 0: TMA + MMA warps (+2 idle), warpgroups 1,2: softmax groups
-constexpr int ATT_BQ = 128;   // rows per softmax group
-constexpr int ATT_BKV = 128;  // keys per block
+constexpr int ATT_BQ = 128;       // rows per softmax group
+constexpr int ATT_BKV = 64;       // keys per block
 constexpr int ATT_D = 64;
-constexpr int ATT_KV_STAGES = 3;
-constexpr int ATT_Q_BYTES = ATT_BQ * ATT_D * 2;       // 16 KB
-constexpr int ATT_KV_BYTES = ATT_BKV * ATT_D * 2;     // 16 KB (K) ; V same
-constexpr int ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;     // 32 KB
-constexpr int ATT_SMEM = 1024 + 2 * ATT_Q_BYTES + ATT_KV_STAGES * 2 * ATT_KV_BYTES + 2 * ATT_P_BYTES + 512;
+constexpr int ATT_KV_STAGES = 6;
+constexpr int ATT_Q_BYTES = ATT_BQ * ATT_D * 2;    // 16 KB
+constexpr int ATT_K_BYTES = ATT_BKV * ATT_D * 2;   // 8 KB (K) ; V same
+constexpr int ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;  // 16 KB per (group, buffer)
+constexpr int ATT_SMEM = 1024 + 2 * ATT_Q_BYTES + ATT_KV_STAGES * 2 * ATT_K_BYTES + 4 * ATT_P_BYTES + 512;
 
 struct alignas(64) AttnParams {
-    CUtensorMap q_map, k_map, v_map;  // 3D (cols, tokens, batch), box (64, 128, 1), SWIZZLE_128B
+    CUtensorMap q_map, k_map, v_map;  // 3D (cols, tokens, batch), box (64, 128 | 64, 1), SWIZZLE_128B
     __half* out;
     int out_ld;
     long long out_bs;
@@ -52,20 +53,25 @@ struct alignas(64) AttnParams {
     int accumulate;
 };
 
+// Pipeline (per 128-row tile g, KV block j, buffer b = j & 1):
+//   MMA:      S_g[b] = Q_g K_j^T  (issued two blocks ahead)   ->  s_full[g][b]
+//   softmax:  read S_g[b], (rare) rescale O_g, P = exp2(S*scale - m), write P_g[b] to smem  ->  p_full[g][b]
+//   MMA:      S_g[b] = Q_g K_{j+2}^T ; O_g += P_g[b] V_j  ->  o_full[g], p_empty[g][b]
+// S and P are double-buffered, so the softmax warps never wait for the tensor core in steady state and vice versa.
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* q_smem = smem;                                  // 2 x 16 KB
-    uint8_t* kv_smem = q_smem + 2 * ATT_Q_BYTES;             // stages x (K 16 KB | V 16 KB)
-    uint8_t* p_smem = kv_smem + ATT_KV_STAGES * 2 * ATT_KV_BYTES;  // 2 x 32 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + 2 * ATT_P_BYTES);
-    uint64_t* q_full = bars;                      // 1
-    uint64_t* kv_full = bars + 1;                 // 3
-    uint64_t* kv_empty = kv_full + ATT_KV_STAGES; // 3
-    uint64_t* s_full = kv_empty + ATT_KV_STAGES;  // 2
-    uint64_t* p_full = s_full + 2;                // 2
-    uint64_t* p_empty = p_full + 2;               // 2
-    uint64_t* o_full = p_empty + 2;               // 2: P.V of the current block has completed (O_g, P_g reusable)
+    uint8_t* q_smem = smem;                                          // 2 x 16 KB
+    uint8_t* kv_smem = q_smem + 2 * ATT_Q_BYTES;                     // stages x (K 8 KB | V 8 KB)
+    uint8_t* p_smem = kv_smem + ATT_KV_STAGES * 2 * ATT_K_BYTES;     // [g][b] x 16 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + 4 * ATT_P_BYTES);
+    uint64_t* q_full = bars;                        // 1
+    uint64_t* kv_full = bars + 1;                   // STAGES
+    uint64_t* kv_empty = kv_full + ATT_KV_STAGES;   // STAGES
+    uint64_t* s_full = kv_empty + ATT_KV_STAGES;    // [g*2 + b]
+    uint64_t* p_full = s_full + 4;                  // [g*2 + b]
+    uint64_t* p_empty = p_full + 4;                 // [g*2 + b]
+    uint64_t* o_full = p_empty + 4;                 // [g]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
     const int warp = threadIdx.x >> 5;
@@ -84,12 +90,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
             mbar_init(&kv_full[i], 1);
             mbar_init(&kv_empty[i], 1);
         }
-        for (int g = 0; g < 2; ++g) {
-            mbar_init(&s_full[g], 1);
-            mbar_init(&p_full[g], 4);
-            mbar_init(&p_empty[g], 1);
-            mbar_init(&o_full[g], 1);
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], 4);
+            mbar_init(&p_empty[i], 1);
         }
+        mbar_init(&o_full[0], 1);
+        mbar_init(&o_full[1], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -97,7 +104,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // TMEM columns: S_g at g*128, O_g at 256 + g*64
+    // TMEM columns: S_g[b] at (g*2 + b)*64, O_g at 256 + g*64
     if (warp < 4) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
       if (warp == 0) {
@@ -112,69 +119,63 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
             const int kb = p.k_b[item], vb = p.v_b[item];
             for (int j = 0; j < nkv; ++j) {
                 mbar_wait(&kv_empty[stage], phase ^ 1);
-                uint8_t* kd = kv_smem + stage * 2 * ATT_KV_BYTES;
-                mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_KV_BYTES);
+                uint8_t* kd = kv_smem + stage * 2 * ATT_K_BYTES;
+                mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_K_BYTES);
                 tma_load_3d(kd, &p.k_map, &kv_full[stage], p.k_col0 + head * ATT_D, j * ATT_BKV, kb);
-                tma_load_3d(kd + ATT_KV_BYTES, &p.v_map, &kv_full[stage], p.v_col0 + head * ATT_D, j * ATT_BKV, vb);
+                tma_load_3d(kd + ATT_K_BYTES, &p.v_map, &kv_full[stage], p.v_col0 + head * ATT_D, j * ATT_BKV, vb);
                 if (++stage == ATT_KV_STAGES) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc_s = umma_idesc_f16(128, ATT_BKV, false, false);  // S = Q K^T
-            constexpr uint32_t idesc_o = umma_idesc_f16(128, ATT_D, false, true);     // O = P V (V is N-major)
-            auto issue_s = [&](int g, int stage) {
+            constexpr uint32_t idesc_o = umma_idesc_f16(128, ATT_D, false, true);     // O += P V (V is N-major)
+            auto issue_s = [&](int g, int jb) {  // scores of block jb into S_g[jb & 1]
+                const int st = jb % ATT_KV_STAGES;
                 const uint64_t a = umma_desc_sw128(smem_u32(q_smem + g * ATT_Q_BYTES), 1024, 16);
-                const uint64_t b = umma_desc_sw128(smem_u32(kv_smem + stage * 2 * ATT_KV_BYTES), 1024, 16);
+                const uint64_t b = umma_desc_sw128(smem_u32(kv_smem + st * 2 * ATT_K_BYTES), 1024, 16);
 #pragma unroll
                 for (int k = 0; k < ATT_D / 16; ++k)
-                    tc_mma_f16_ss(tmem_base + g * 128, a + 2 * k, b + 2 * k, idesc_s, k > 0);
-                tc_commit(&s_full[g]);
+                    tc_mma_f16_ss(tmem_base + (g * 2 + (jb & 1)) * 64, a + 2 * k, b + 2 * k, idesc_s, k > 0);
+                tc_commit(&s_full[g * 2 + (jb & 1)]);
             };
+            auto wait_kv = [&](int jb) { mbar_wait(&kv_full[jb % ATT_KV_STAGES], (jb / ATT_KV_STAGES) & 1); };
             mbar_wait(q_full, 0);
-            mbar_wait(&kv_full[0], 0);
-            tc_fence_after();
-            issue_s(0, 0);
-            issue_s(1, 0);
-            int stage = 0;
-            uint32_t phase = 0;
+            for (int jb = 0; jb < 2 && jb < nkv; ++jb) {
+                wait_kv(jb);
+                tc_fence_after();
+                issue_s(0, jb);
+                issue_s(1, jb);
+            }
             for (int j = 0; j < nkv; ++j) {
-                int nstage = stage + 1;
-                uint32_t nphase = phase;
-                if (nstage == ATT_KV_STAGES) {
-                    nstage = 0;
-                    nphase ^= 1;
-                }
+                const int b = j & 1;
+                const int st = j % ATT_KV_STAGES;
                 for (int g = 0; g < 2; ++g) {
-                    mbar_wait(&p_full[g], j & 1);  // P_g(j) is in smem and S_g has been read out
+                    mbar_wait(&p_full[g * 2 + b], (j >> 1) & 1);  // P_g[b] is in smem and S_g[b] has been read out
                     tc_fence_after();
-                    // S_g(j+1) first: it is what the softmax group waits for next; P.V(j) only has to land before
-                    // the next block's probabilities overwrite the P buffer
-                    if (j + 1 < nkv) {
-                        mbar_wait(&kv_full[nstage], nphase);
+                    if (j + 2 < nkv) {  // refill the score buffer that was just released
+                        wait_kv(j + 2);
                         tc_fence_after();
-                        issue_s(g, nstage);
+                        issue_s(g, j + 2);
                     }
-                    const uint32_t p_addr = smem_u32(p_smem + g * ATT_P_BYTES);
-                    const uint32_t v_addr = smem_u32(kv_smem + stage * 2 * ATT_KV_BYTES + ATT_KV_BYTES);
+                    const uint32_t p_addr = smem_u32(p_smem + (g * 2 + b) * ATT_P_BYTES);
+                    const uint32_t v_addr = smem_u32(kv_smem + st * 2 * ATT_K_BYTES + ATT_K_BYTES);
                     const uint32_t d_tmem = tmem_base + 256 + g * 64;
 #pragma unroll
                     for (int k = 0; k < ATT_BKV / 16; ++k) {
-                        // A = P: K-major, two 64-wide (16 KB) halves; B = V: 16 key rows (2 KB) per K step
-                        const uint64_t a = umma_desc_sw128(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 1024, 16);
-                        const uint64_t b = umma_desc_sw128(v_addr + k * 2048, 1024, 1024);
-                        tc_mma_f16_ss(d_tmem, a, b, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                        // A = P: K-major 64-wide panel; B = V: 16 key rows (2 KB) per K step, N-major
+                        const uint64_t a = umma_desc_sw128(p_addr + k * 32, 1024, 16);
+                        const uint64_t bd = umma_desc_sw128(v_addr + k * 2048, 1024, 1024);
+                        tc_mma_f16_ss(d_tmem, a, bd, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit(&o_full[g]);
-                    tc_commit(&p_empty[g]);
+                    tc_commit(&p_empty[g * 2 + b]);
                 }
-                tc_commit(&kv_empty[stage]);
-                stage = nstage;
-                phase = nphase;
+                tc_commit(&kv_empty[st]);
             }
         }
       }
@@ -186,31 +187,32 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t s_tmem = tmem_base + g * 128 + lane_base;
-        // this row's 16 B chunk slots inside a 128 B swizzled row: slot(t) = (t ^ (row & 7)) * 16
-        const uint32_t my_p = smem_u32(p_smem + g * ATT_P_BYTES) + row * 128;
-        const uint32_t sw = (uint32_t)(row & 7) << 4;
         const uint32_t o_tmem = tmem_base + 256 + g * 64 + lane_base;
+        // this row's 16 B chunk slots inside a 128 B swizzled row: slot(t) = (t ^ (row & 7)) * 16
+        const uint32_t my_p = smem_u32(p_smem + g * 2 * ATT_P_BYTES) + row * 128;
+        const uint32_t sw = (uint32_t)(row & 7) << 4;
         float m = -INFINITY, l = 0.f;
         constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P may reach 2^8 before O is rescaled
 
         for (int j = 0; j < nkv; ++j) {
-            mbar_wait(&s_full[g], j & 1);
+            const int b = j & 1;
+            mbar_wait(&s_full[g * 2 + b], (j >> 1) & 1);
             tc_fence_after();
             const int kv_left = p.n_kv - j * ATT_BKV;  // valid keys in this block (>= 1)
-            uint32_t sr[4][32];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_tmem + c * 32, sr[c]);
+            uint32_t sr[2][32];
+            tmem_ld_32x32(s_tmem + b * 64, sr[0]);
+            tmem_ld_32x32(s_tmem + b * 64 + 32, sr[1]);
             tc_wait_ld();
             if (kv_left < ATT_BKV) {  // partial last block: keys beyond n_kv (zero-filled K rows) are excluded
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < 2; ++c)
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         if (c * 32 + i >= kv_left) sr[c][i] = __float_as_uint(-INFINITY);
             }
             float mx = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
             const float m_cand = fmaxf(m, mx * p.scale_log2);
@@ -237,11 +239,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
                     tc_wait_st();
                 }
             }
-            // the P buffer must have been consumed by the previous block's P.V
-            mbar_wait(&p_empty[g], (j & 1) ^ 1);
+            // P_g[b] must have been consumed by P.V(j-2)
+            mbar_wait(&p_empty[g * 2 + b], ((j >> 1) & 1) ^ 1);
             float sum = 0.f;
+            const uint32_t rowp = my_p + b * ATT_P_BYTES;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -252,18 +255,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
                     sum += p0 + p1;
                     pk[i] = pack_half2(p0, p1);
                 }
-                // K-major SWIZZLE_128B: half hh = c >> 1, 16 B chunk index within the 128 B row = (c & 1) * 4 + t
-                const uint32_t rowp = my_p + (c >> 1) * 16384;
+                // K-major SWIZZLE_128B: 16 B chunk index within the 128 B row = c * 4 + t
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
-                    st_shared_v4(rowp + ((((c & 1) * 4 + t) << 4) ^ sw), pk[4 * t], pk[4 * t + 1], pk[4 * t + 2],
+                    st_shared_v4(rowp + (((c * 4 + t) << 4) ^ sw), pk[4 * t], pk[4 * t + 1], pk[4 * t + 2],
                                  pk[4 * t + 3]);
             }
             l += sum;
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[g]);
+            if (lane == 0) mbar_arrive(&p_full[g * 2 + b]);
         }
         // all P.V of this tile have landed
         mbar_wait(&o_full[g], (nkv - 1) & 1);
@@ -311,10 +313,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-static int make_attn_map(CUtensorMap* m, const void* ptr, int cols, int ld, int tokens, long long bs, int nb) {
+static int make_attn_map(CUtensorMap* m, const void* ptr, int cols, int ld, int tokens, long long bs, int nb,
+                         uint32_t box_rows) {
     const uint64_t dims[3] = {(uint64_t)cols, (uint64_t)tokens, (uint64_t)nb};
     const uint64_t strides[3] = {1, (uint64_t)ld, (uint64_t)bs};
-    const uint32_t box[3] = {64, 128, 1};
+    const uint32_t box[3] = {64, box_rows, 1};
     return make_tmap_f16(m, ptr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
@@ -352,9 +355,9 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
                   "omg_attention: negative batch index in item %d", i);
     }
     const int cols = d->heads * 64;
-    if (make_attn_map(&p.q_map, d->q, d->q_col0 + cols, d->q_ld, d->n_q, d->q_bs, max_qb + 1)) return 1;
-    if (make_attn_map(&p.k_map, d->k, d->k_col0 + cols, d->k_ld, d->n_kv, d->k_bs, max_kb + 1)) return 1;
-    if (make_attn_map(&p.v_map, d->v, d->v_col0 + cols, d->v_ld, d->n_kv, d->v_bs, max_vb + 1)) return 1;
+    if (make_attn_map(&p.q_map, d->q, d->q_col0 + cols, d->q_ld, d->n_q, d->q_bs, max_qb + 1, ATT_BQ)) return 1;
+    if (make_attn_map(&p.k_map, d->k, d->k_col0 + cols, d->k_ld, d->n_kv, d->k_bs, max_kb + 1, ATT_BKV)) return 1;
+    if (make_attn_map(&p.v_map, d->v, d->v_col0 + cols, d->v_ld, d->n_kv, d->v_bs, max_vb + 1, ATT_BKV)) return 1;
     p.out = static_cast<__half*>(d->out);
     p.out_ld = d->out_ld;
     p.out_bs = d->out_bs;
