@@ -17,8 +17,9 @@
 // the running P.V accumulator of each tile).
 // Softmax follows the lazy-rescale scheme: O stays in TMEM and is accumulated by the tensor core across KV blocks;
 // the running maximum is allowed to go stale by up to 2^8 and O is only rescaled (TMEM load-scale-store) when a row
-// maximum grows beyond that, which after the first blocks is rare.  exp2 runs on the MUFU for 3 of 4 elements and as
-// a degree-3 polynomial on the FMA pipe for the 4th (the MUFU is the bottleneck unit at head_dim 64).
+// maximum grows beyond that, which after the first blocks is rare.  The kernel is issue-slot bound (ncu: issue 58 %,
+// MUFU 42 %, tensor 28 % at N = 4096), so every exp2 stays on the MUFU (a polynomial on the FMA pipe costs 8 issue
+// slots per element and made it slower).
 #include <cuda_fp16.h>
 #include <math.h>
 #include <string.h>
@@ -56,7 +57,7 @@ struct alignas(64) AttnParams {
 // Pipeline (per 128-row tile g, KV block j, buffer b = j & 1):
 //   MMA:      S_g[b] = Q_g K_j^T  (issued two blocks ahead)   ->  s_full[g][b]
 //   softmax:  read S_g[b], (rare) rescale O_g, P = exp2(S*scale - m), write P_g[b] to smem  ->  p_full[g][b]
-//   MMA:      S_g[b] = Q_g K_{j+2}^T ; O_g += P_g[b] V_j  ->  o_full[g], p_empty[g][b]
+//   MMA:      S_g[b] = Q_g K_{j+2}^T ; O_g += P_g[b] V_j  ->  p_empty[g][b]
 // S and P are double-buffered, so the softmax warps never wait for the tensor core in steady state and vice versa.
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -70,9 +71,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
     uint64_t* kv_empty = kv_full + ATT_KV_STAGES;   // STAGES
     uint64_t* s_full = kv_empty + ATT_KV_STAGES;    // [g*2 + b]
     uint64_t* p_full = s_full + 4;                  // [g*2 + b]
-    uint64_t* p_empty = p_full + 4;                 // [g*2 + b]
-    uint64_t* o_full = p_empty + 4;                 // [g]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+    uint64_t* p_empty = p_full + 4;                 // [g*2 + b]: P.V of the block that used buffer b has completed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -88,15 +88,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
         mbar_init(q_full, 1);
         for (int i = 0; i < ATT_KV_STAGES; ++i) {
             mbar_init(&kv_full[i], 1);
-            mbar_init(&kv_empty[i], 1);
+            mbar_init(&kv_empty[i], 2);  // one commit per tile's MMA issuer
         }
         for (int i = 0; i < 4; ++i) {
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], 4);
             mbar_init(&p_empty[i], 1);
         }
-        mbar_init(&o_full[0], 1);
-        mbar_init(&o_full[1], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -129,18 +127,24 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
                 }
             }
         }
-      } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
+      } else if (warp == 1 || warp == 2) {
+        // ------------------------------------------------------------------ MMA issuers: warp 1 -> tile 0, warp 2 -> tile 1
+        // (a single issuing thread would serialise both tiles' barrier round-trips; the tensor work per event is
+        // only 256 cycles)
         if (lane == 0) {
+            const int g = warp - 1;
             constexpr uint32_t idesc_s = umma_idesc_f16(128, ATT_BKV, false, false);  // S = Q K^T
             constexpr uint32_t idesc_o = umma_idesc_f16(128, ATT_D, false, true);     // O += P V (V is N-major)
-            auto issue_s = [&](int g, int jb) {  // scores of block jb into S_g[jb & 1]
-                const int st = jb % ATT_KV_STAGES;
-                const uint64_t a = umma_desc_sw128(smem_u32(q_smem + g * ATT_Q_BYTES), 1024, 16);
-                const uint64_t b = umma_desc_sw128(smem_u32(kv_smem + st * 2 * ATT_K_BYTES), 1024, 16);
+            const uint64_t q_desc = umma_desc_sw128(smem_u32(q_smem + g * ATT_Q_BYTES), 1024, 16);
+            const uint64_t k_desc0 = umma_desc_sw128(smem_u32(kv_smem), 1024, 16);
+            const uint64_t v_desc0 = umma_desc_sw128(smem_u32(kv_smem + ATT_K_BYTES), 1024, 1024);
+            const uint64_t p_desc0 = umma_desc_sw128(smem_u32(p_smem + g * 2 * ATT_P_BYTES), 1024, 16);
+            const uint32_t o_tmem_g = tmem_base + 256 + g * 64;
+            auto issue_s = [&](int jb) {  // scores of block jb into S_g[jb & 1]
+                const uint64_t kd = k_desc0 + (uint64_t)((jb % ATT_KV_STAGES) * ((2 * ATT_K_BYTES) >> 4));
 #pragma unroll
                 for (int k = 0; k < ATT_D / 16; ++k)
-                    tc_mma_f16_ss(tmem_base + (g * 2 + (jb & 1)) * 64, a + 2 * k, b + 2 * k, idesc_s, k > 0);
+                    tc_mma_f16_ss(tmem_base + (g * 2 + (jb & 1)) * 64, q_desc + 2 * k, kd + 2 * k, idesc_s, k > 0);
                 tc_commit(&s_full[g * 2 + (jb & 1)]);
             };
             auto wait_kv = [&](int jb) { mbar_wait(&kv_full[jb % ATT_KV_STAGES], (jb / ATT_KV_STAGES) & 1); };
@@ -148,33 +152,26 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
             for (int jb = 0; jb < 2 && jb < nkv; ++jb) {
                 wait_kv(jb);
                 tc_fence_after();
-                issue_s(0, jb);
-                issue_s(1, jb);
+                issue_s(jb);
             }
             for (int j = 0; j < nkv; ++j) {
                 const int b = j & 1;
                 const int st = j % ATT_KV_STAGES;
-                for (int g = 0; g < 2; ++g) {
-                    mbar_wait(&p_full[g * 2 + b], (j >> 1) & 1);  // P_g[b] is in smem and S_g[b] has been read out
+                mbar_wait(&p_full[g * 2 + b], (j >> 1) & 1);  // P_g[b] is in smem and S_g[b] has been read out
+                tc_fence_after();
+                if (j + 2 < nkv) {  // refill the score buffer that was just released
+                    wait_kv(j + 2);
                     tc_fence_after();
-                    if (j + 2 < nkv) {  // refill the score buffer that was just released
-                        wait_kv(j + 2);
-                        tc_fence_after();
-                        issue_s(g, j + 2);
-                    }
-                    const uint32_t p_addr = smem_u32(p_smem + (g * 2 + b) * ATT_P_BYTES);
-                    const uint32_t v_addr = smem_u32(kv_smem + st * 2 * ATT_K_BYTES + ATT_K_BYTES);
-                    const uint32_t d_tmem = tmem_base + 256 + g * 64;
-#pragma unroll
-                    for (int k = 0; k < ATT_BKV / 16; ++k) {
-                        // A = P: K-major 64-wide panel; B = V: 16 key rows (2 KB) per K step, N-major
-                        const uint64_t a = umma_desc_sw128(p_addr + k * 32, 1024, 16);
-                        const uint64_t bd = umma_desc_sw128(v_addr + k * 2048, 1024, 1024);
-                        tc_mma_f16_ss(d_tmem, a, bd, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-                    }
-                    tc_commit(&o_full[g]);
-                    tc_commit(&p_empty[g * 2 + b]);
+                    issue_s(j + 2);
                 }
+                const uint64_t pd = p_desc0 + (uint64_t)(b * (ATT_P_BYTES >> 4));
+                const uint64_t vd = v_desc0 + (uint64_t)(st * ((2 * ATT_K_BYTES) >> 4));
+#pragma unroll
+                for (int k = 0; k < ATT_BKV / 16; ++k) {
+                    // A = P: K-major 64-wide panel (+32 B per K step); B = V: 16 key rows (2 KB) per K step, N-major
+                    tc_mma_f16_ss(o_tmem_g, pd + 2 * k, vd + 128 * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                }
+                tc_commit(&p_empty[g * 2 + b]);
                 tc_commit(&kv_empty[st]);
             }
         }
@@ -221,8 +218,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
             } else {
                 const bool need = (m_cand - m) > kRescaleThreshold;
                 if (__any_sync(0xffffffffu, need)) {
-                    // O_g holds blocks < j relative to the stale maximum: rescale it once P.V(j-1) has landed
-                    mbar_wait(&o_full[g], (j - 1) & 1);
+                    // O_g holds blocks < j relative to the stale maximum: rescale it once P.V(j-1) has landed.
+                    // (p_empty of the OTHER buffer: this is next block's regular wait done early, so no mbarrier
+                    // phase is skipped - a waiter may never fall two phases behind a parity barrier.)
+                    mbar_wait(&p_empty[g * 2 + (b ^ 1)], ((j - 1) >> 1) & 1);
                     tc_fence_after();
                     const float corr = need ? fast_exp2(m - m_cand) : 1.0f;
                     if (need) m = m_cand;
@@ -251,7 +250,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
                     const float x0 = fmaf(__uint_as_float(sr[c][2 * i]), p.scale_log2, -m);
                     const float x1 = fmaf(__uint_as_float(sr[c][2 * i + 1]), p.scale_log2, -m);
                     const float p0 = fast_exp2(x0);
-                    const float p1 = (i & 1) ? poly_exp2(x1) : fast_exp2(x1);
+                    const float p1 = fast_exp2(x1);
                     sum += p0 + p1;
                     pk[i] = pack_half2(p0, p1);
                 }
@@ -267,8 +266,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[g * 2 + b]);
         }
-        // all P.V of this tile have landed
-        mbar_wait(&o_full[g], (nkv - 1) & 1);
+        // all P.V of this tile have landed: the last user of each P buffer
+        if (nkv >= 2) mbar_wait(&p_empty[g * 2 + ((nkv - 2) & 1)], ((nkv - 2) >> 1) & 1);
+        mbar_wait(&p_empty[g * 2 + ((nkv - 1) & 1)], ((nkv - 1) >> 1) & 1);
         tc_fence_after();
         float o_acc[ATT_D];
 #pragma unroll
