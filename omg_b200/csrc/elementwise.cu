@@ -9,6 +9,7 @@
 
 #include "../../include/omg_b200.h"
 #include "host_common.h"
+#include "ptx.cuh"
 
 namespace omg {
 
@@ -33,6 +34,8 @@ __device__ __forceinline__ void load4(const __half* p, float (&v)[4]) {
 }
 
 __global__ void fuse_step_kernel(FuseParams p) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= p.HW) return;
     const size_t HW = p.HW;
@@ -115,6 +118,8 @@ __global__ void fuse_step_kernel(FuseParams p) {
 // out[b, w, :] = sum_n coef[w, n] * ctx[b, n, :]   (coef = M diag(alpha) or diag(1 - alpha); L = 77)
 __global__ void ctx_mix_kernel(const __half* __restrict__ ctx, const float* __restrict__ coef, __half* __restrict__ out,
                                int L, int C) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int b = blockIdx.z, w = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -128,6 +133,8 @@ __global__ void ctx_mix_kernel(const __half* __restrict__ ctx, const float* __re
 
 __global__ void axpy_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, float alpha,
                             uint4* __restrict__ y, long long nvec) {
+    griddep_launch_dependents();
+    griddep_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nvec) return;
     const uint4 ua = a[i], ub = b[i];
@@ -151,9 +158,8 @@ extern "C" int omg_axpy(const void* a, const void* b, float alpha, void* y, long
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     OMG_CHECK(a && b && y && n > 0 && n % 8 == 0, "omg_axpy: bad arguments");
     const long long nvec = n / 8;
-    axpy_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, stream>>>(static_cast<const uint4*>(a),
-                                                                     static_cast<const uint4*>(b), alpha,
-                                                                     static_cast<uint4*>(y), nvec);
+    OMG_CUDA(launch_pdl(axpy_kernel, dim3((unsigned)((nvec + 255) / 256)), dim3(256), 0, stream,
+                        static_cast<const uint4*>(a), static_cast<const uint4*>(b), alpha, static_cast<uint4*>(y), nvec));
     return check_launch("axpy_kernel");
 }
 
@@ -180,14 +186,14 @@ extern "C" int omg_fuse_step(const omg_fuse_desc* d, void* stream_) {
     p.next_concept_in = static_cast<__half*>(d->next_concept_in);
     p.latents_f16 = static_cast<__half*>(d->latents_f16);
     p.HW = d->HW;
-    fuse_step_kernel<<<(d->HW + 127) / 128, 128, 0, stream>>>(p);
+    OMG_CUDA(launch_pdl(fuse_step_kernel, dim3((d->HW + 127) / 128), dim3(128), 0, stream, p));
     return check_launch("fuse_step_kernel");
 }
 
 extern "C" int omg_ctx_mix(const void* ctx, const void* coef, void* out, int B, int L, int C, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     OMG_CHECK(ctx && coef && out && B >= 1 && L >= 1 && C >= 1, "omg_ctx_mix: bad arguments");
-    ctx_mix_kernel<<<dim3((C + 127) / 128, L, B), 128, 0, stream>>>(
-        static_cast<const __half*>(ctx), static_cast<const float*>(coef), static_cast<__half*>(out), L, C);
+    OMG_CUDA(launch_pdl(ctx_mix_kernel, dim3((C + 127) / 128, L, B), dim3(128), 0, stream,
+                        static_cast<const __half*>(ctx), static_cast<const float*>(coef), static_cast<__half*>(out), L, C));
     return check_launch("ctx_mix_kernel");
 }

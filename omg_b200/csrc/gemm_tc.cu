@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();  // the prologue above overlaps the previous kernel's tail
+    griddep_wait();               // operands / residual / output buffers belong to earlier kernels until here
 
     if (warp == 0) {
         // ------------------------------------------------------------- TMA producer
@@ -357,7 +359,7 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
     }
     const int total = p.m_tiles * p.n_tiles;
     const int grid = std::min(total, num_sms);
-    gemm_tc_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+    OMG_CUDA(launch_pdl(gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, p));
     return check_launch("gemm_tc_kernel");
 }
 

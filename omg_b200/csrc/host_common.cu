@@ -1,5 +1,7 @@
 #include "host_common.h"
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "../../include/omg_b200.h"
@@ -8,6 +10,15 @@ namespace omg {
 
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("OMG_NO_PDL");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
 
 PFN_encodeTiled get_encode_tiled() {
     static PFN_encodeTiled fn = nullptr;

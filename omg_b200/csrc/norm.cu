@@ -9,6 +9,7 @@
 
 #include "../../include/omg_b200.h"
 #include "host_common.h"
+#include "ptx.cuh"
 
 namespace omg {
 
@@ -30,6 +31,8 @@ __device__ __forceinline__ uint4 gn_load8(const GnSrc& s, size_t pix, int c) {
 // Identical images in a batch therefore get bit-identical results (the reference's stage-1 rows are identical).
 __global__ void gn_partial_kernel(GnSrc s, int HW, int cpg, int rows_per_cta, float* __restrict__ partial) {
     extern __shared__ float s_red[];  // [rows_par][C] sums, then [rows_par][C] squares
+    griddep_launch_dependents();
+    griddep_wait();
     const int C = s.C1 + s.C2;
     const int b = blockIdx.y;
     const int c = threadIdx.x * 8;
@@ -99,6 +102,8 @@ __global__ void gn_partial_kernel(GnSrc s, int HW, int cpg, int rows_per_cta, fl
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int splits, float inv_n, float eps,
                                    float* __restrict__ stats) {
     const int b = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;  // block = 32 groups x 32 lanes
+    griddep_launch_dependents();
+    griddep_wait();
     float sa = 0.f, sq = 0.f;
     for (int k = lane; k < splits; k += 32) {
         const float2 p = *reinterpret_cast<const float2*>(partial + (((size_t)b * splits + k) * 32 + g) * 2);
@@ -122,6 +127,8 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int splits
 __global__ void gn_apply_kernel(GnSrc s, int HW, int cpg, int silu, const float* __restrict__ stats,
                                 const __half* __restrict__ gamma, const __half* __restrict__ beta,
                                 __half* __restrict__ y) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int C = s.C1 + s.C2;
     const int vec_per_row = C / 8;
     const int b = blockIdx.y;
@@ -181,6 +188,8 @@ template <int MAX_VEC>
 __global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
                                  const __half* __restrict__ beta, __half* __restrict__ y, long long rows, int C,
                                  float eps) {
+    griddep_launch_dependents();
+    griddep_wait();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -280,14 +289,15 @@ extern "C" int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int
         OMG_CUDA(cudaFuncSetAttribute(gn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4));  // ty * C <= 1024 * 8
         configured = true;
     }
-    gn_partial_kernel<<<dim3(splits, B), dim3(tx, ty), smem, stream>>>(s, HW, cpg, rows_per_cta, partial);
+    OMG_CUDA(launch_pdl(gn_partial_kernel, dim3(splits, B), dim3(tx, ty), smem, stream, s, HW, cpg, rows_per_cta, partial));
     if (check_launch("gn_partial_kernel")) return 1;
-    gn_finalize_kernel<<<B, 1024, 0, stream>>>(partial, splits, 1.0f / ((float)HW * (float)cpg), eps, stats);
+    OMG_CUDA(launch_pdl(gn_finalize_kernel, dim3(B), dim3(1024), 0, stream, (const float*)partial, splits,
+                        1.0f / ((float)HW * (float)cpg), eps, stats));
     if (check_launch("gn_finalize_kernel")) return 1;
     const size_t nvec = (size_t)HW * (C / 8);
-    gn_apply_kernel<<<dim3((unsigned)((nvec + 511) / 512), B), 256, 0, stream>>>(
-        s, HW, cpg, silu, stats, static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
-        static_cast<__half*>(y));
+    OMG_CUDA(launch_pdl(gn_apply_kernel, dim3((unsigned)((nvec + 511) / 512), B), dim3(256), 0, stream, s, HW, cpg, silu,
+                        (const float*)stats, static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
+                        static_cast<__half*>(y)));
     return check_launch("gn_apply_kernel");
 }
 
@@ -300,20 +310,15 @@ extern "C" int omg_layernorm(const void* x, const void* gamma, const void* beta,
     const int warps = 8;
     const unsigned grid = (unsigned)((rows + warps - 1) / warps);
     const int nvec = C / 8;
+    const __half* xp = static_cast<const __half*>(x);
+    const __half* gp = static_cast<const __half*>(gamma);
+    const __half* bp = static_cast<const __half*>(beta);
+    __half* yp = static_cast<__half*>(y);
     if (nvec <= 96)
-        layernorm_kernel<3><<<grid, warps * 32, 0, stream>>>(static_cast<const __half*>(x),
-                                                             static_cast<const __half*>(gamma),
-                                                             static_cast<const __half*>(beta),
-                                                             static_cast<__half*>(y), rows, C, eps);
+        OMG_CUDA(launch_pdl(layernorm_kernel<3>, dim3(grid), dim3(warps * 32), 0, stream, xp, gp, bp, yp, rows, C, eps));
     else if (nvec <= 160)
-        layernorm_kernel<5><<<grid, warps * 32, 0, stream>>>(static_cast<const __half*>(x),
-                                                             static_cast<const __half*>(gamma),
-                                                             static_cast<const __half*>(beta),
-                                                             static_cast<__half*>(y), rows, C, eps);
+        OMG_CUDA(launch_pdl(layernorm_kernel<5>, dim3(grid), dim3(warps * 32), 0, stream, xp, gp, bp, yp, rows, C, eps));
     else
-        layernorm_kernel<10><<<grid, warps * 32, 0, stream>>>(static_cast<const __half*>(x),
-                                                              static_cast<const __half*>(gamma),
-                                                              static_cast<const __half*>(beta),
-                                                              static_cast<__half*>(y), rows, C, eps);
+        OMG_CUDA(launch_pdl(layernorm_kernel<10>, dim3(grid), dim3(warps * 32), 0, stream, xp, gp, bp, yp, rows, C, eps));
     return check_launch("layernorm_kernel");
 }
