@@ -65,9 +65,31 @@ typedef struct {
     int32_t residual_ld;
     int32_t epilogue;
     int32_t block_n;    /* 0 = auto; else 64 | 128 | 160 | 256 */
+    /* LayerNorm folded into a GEMM pair (BasicTransformerBlock norm1/2/3 [3P] followed by to_q|k|v / ff.net.0.proj):
+     * the GEMM that PRODUCES the hidden state h writes per-row partial (sum, sum of squares) of its output, one
+     * partial per n-tile, to row_stats_out [n_tiles][rows][2] fp32; the GEMM that CONSUMES LayerNorm(h) runs on raw h
+     * with gamma folded into its weights and finishes  out = rstd * (acc - mean * c1[n]) + c2[n]  in the epilogue,
+     * c1 = row sums of the folded fp16 weights, c2 = W beta + bias (fp32 [N]).  No LayerNorm kernel, no normalised
+     * copy of h.  ln_dim = channels of h; row_stats_parts = n-tiles of the producer (omg_gemm_plan). */
+    void* row_stats_out;
+    const void* row_stats_in;
+    int32_t row_stats_parts;
+    int64_t row_stats_stride; /* rows per partial plane (0 = rows of this GEMM); lets a row-sliced GEMM index the full buffer */
+    int32_t ln_dim;
+    float ln_eps;
+    const void* col_c1;
+    const void* col_c2;
+    /* multi-stream launches: streams (row groups) with different LoRA sets have different c1/c2; then col_c1/col_c2
+     * are [n_col_groups][N] and rows [col_group_end[g-1], col_group_end[g]) use plane g (boundaries % 128 == 0). */
+    int32_t n_col_groups;
+    int64_t col_group_end[8];
 } omg_gemm_desc;
 
 int omg_gemm(const omg_gemm_desc* desc, void* stream);
+
+/* Tile plan omg_gemm will use for an output grid (W, H, B) with N channels: block_n and the number of n-tiles
+ * (= row_stats_parts for a consumer of this GEMM's row statistics). */
+int omg_gemm_plan(int N, int epilogue, int W, int H, int B, int* block_n, int* n_tiles);
 
 #define OMG_ATTN_MAX_ITEMS 16
 

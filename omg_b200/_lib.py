@@ -28,7 +28,10 @@ class GemmDesc(C.Structure):
                 ("w", C.c_void_p), ("N", C.c_int32), ("Ktot", C.c_int32), ("w2", C.c_void_p), ("K2tot", C.c_int32),
                 ("d", View4), ("bias", C.c_void_p),
                 ("rowvec", C.c_void_p), ("rowvec_ld", C.c_int32), ("residual", C.c_void_p),
-                ("residual_ld", C.c_int32), ("epilogue", C.c_int32), ("block_n", C.c_int32)]
+                ("residual_ld", C.c_int32), ("epilogue", C.c_int32), ("block_n", C.c_int32),
+                ("row_stats_out", C.c_void_p), ("row_stats_in", C.c_void_p), ("row_stats_parts", C.c_int32),
+                ("row_stats_stride", C.c_int64), ("ln_dim", C.c_int32), ("ln_eps", C.c_float), ("col_c1", C.c_void_p), ("col_c2", C.c_void_p),
+                ("n_col_groups", C.c_int32), ("col_group_end", C.c_int64 * 8)]
 
 
 class AttnDesc(C.Structure):
@@ -54,6 +57,7 @@ class FuseDesc(C.Structure):
 # every symbol include/omg_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "omg_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "omg_gemm_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "omg_attention": (C.c_int, [C.POINTER(AttnDesc), C.c_void_p]),
     "omg_groupnorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

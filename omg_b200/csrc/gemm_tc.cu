@@ -50,6 +50,17 @@ struct alignas(64) GemmParams {
     const __half* residual;
     int residual_ld;
     int act_silu;
+    // LayerNorm folded into the GEMM pair (see omg_gemm_desc): statistics written by the producer's epilogue ...
+    float* stats_out;          // [n_tiles][rows][2] partial (sum, sum of squares) of this GEMM's output rows, or null
+    // ... and consumed by the next GEMM's epilogue: out = rstd * (acc - mean * c1[n]) + c2[n]
+    const float* stats_in;     // [stats_parts][rows][2] or null
+    int stats_parts;
+    long long stats_rows;      // rows per part (both directions)
+    float ln_inv_dim, ln_eps;
+    const float* col_c1;       // [N] fp32: row sums of the gamma-folded weights
+    const float* col_c2;       // [N] fp32: W beta + bias
+    int n_col_groups;          // c1/c2 are [n_col_groups][N]; row group g = rows [col_group_end[g-1], col_group_end[g])
+    long long col_group_end[8];
 };
 
 template <int BN>
@@ -57,10 +68,10 @@ struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - STAGING_BYTES - 256 * 4 /*bias*/ - 256 /*bars*/;
+    static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - STAGING_BYTES - 2 * 256 * 4 /*bias, c1*/ - 256 /*bars*/;
     static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + 256 * 4 + 256;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + 2 * 256 * 4 + 256;
     static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator stage
     static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
 };
@@ -75,7 +86,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
     float* s_bias = reinterpret_cast<float*>(staging + STAGING_BYTES);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + 256);
+    float* s_c1 = s_bias + 256;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_c1 + 256);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -196,20 +208,49 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             const int n0 = n_tile * BN;
 
             asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's s_bias readers are done
+            const bool ln = p.stats_in != nullptr;
+            // tiles never straddle row groups (host guarantees 128-row alignment): pick this tile's c1/c2 plane
+            size_t cg = 0;
+            if (ln && p.n_col_groups > 1) {
+                const long long tile_pix0 = ((long long)b * p.img_h + h0) * p.img_w + w0;
+                for (int g2 = 0; g2 + 1 < p.n_col_groups; ++g2)
+                    if (tile_pix0 >= p.col_group_end[g2]) cg = g2 + 1;
+                cg *= (size_t)p.N;
+            }
             for (int j = et; j < BN; j += 128) {
-                float v = 0.f;
+                float v = 0.f, c1 = 0.f;
                 const int n = n0 + j;
                 if (n < p.N) {
-                    if (p.bias) v += __half2float(p.bias[n]);
-                    if (p.rowvec) v += __half2float(p.rowvec[(size_t)b * p.rowvec_ld + n]);
+                    if (ln) {
+                        v = p.col_c2[cg + n];
+                        c1 = p.col_c1[cg + n];
+                    } else {
+                        if (p.bias) v += __half2float(p.bias[n]);
+                        if (p.rowvec) v += __half2float(p.rowvec[(size_t)b * p.rowvec_ld + n]);
+                    }
                 }
                 s_bias[j] = v;
+                s_c1[j] = c1;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
 
             const int ph = h0 + et / p.tw, pw = w0 + et % p.tw;
             const bool row_valid = (ph < p.img_h) && (pw < p.img_w);
             const size_t pix = ((size_t)b * p.img_h + ph) * p.img_w + pw;
+            // folded LayerNorm: this row's mean / rstd from the producer's per-n-tile partial sums (one row per
+            // thread, so no cross-thread reduction is needed); out = rstd * (acc - mean * c1) + c2
+            float ln_a = 1.0f, ln_mu = 0.f;  // value = ln_a * (acc - ln_mu * c1) + c2
+            if (ln && row_valid) {
+                float sa = 0.f, sq = 0.f;
+                for (int t = 0; t < p.stats_parts; ++t) {
+                    const float2 st = __ldg(reinterpret_cast<const float2*>(p.stats_in) + (size_t)t * p.stats_rows + pix);
+                    sa += st.x;
+                    sq += st.y;
+                }
+                ln_mu = sa * p.ln_inv_dim;
+                ln_a = rsqrtf(fmaxf(sq * p.ln_inv_dim - ln_mu * ln_mu, 0.f) + p.ln_eps);
+            }
+            float row_sum = 0.f, row_sq = 0.f;  // statistics of THIS GEMM's output row (stats_out)
             // pixel origin of this warp's 32-row store box
             const int sh = h0 + (q * 32) / p.tw, sw = w0 + (q * 32) % p.tw;
 
@@ -246,14 +287,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     tmem_ld_32x32(t_row + c * 64 + 32, r1);
                     tc_wait_ld();
                     const float* sb = s_bias + c * 64;
+                    const float* sc = s_c1 + c * 64;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float o[2];
 #pragma unroll
                         for (int t = 0; t < 2; ++t) {
                             const int i = 4 * j + 2 * t;  // column of the (value, gate) pair
-                            const float a = __uint_as_float(r0[i]) + sb[i];
-                            const float g = __uint_as_float(r0[i + 1]) + sb[i + 1];
+                            const float a = ln_a * (__uint_as_float(r0[i]) - ln_mu * sc[i]) + sb[i];
+                            const float g = ln_a * (__uint_as_float(r0[i + 1]) - ln_mu * sc[i + 1]) + sb[i + 1];
                             o[t] = a * gelu_erf(g);
                         }
                         outp[j] = pack_half2(o[0], o[1]);
@@ -264,8 +306,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                         for (int t = 0; t < 2; ++t) {
                             const int i = 4 * j + 2 * t;
-                            const float a = __uint_as_float(r1[i]) + sb[32 + i];
-                            const float g = __uint_as_float(r1[i + 1]) + sb[32 + i + 1];
+                            const float a = ln_a * (__uint_as_float(r1[i]) - ln_mu * sc[32 + i]) + sb[32 + i];
+                            const float g = ln_a * (__uint_as_float(r1[i + 1]) - ln_mu * sc[32 + i + 1]) + sb[32 + i + 1];
                             o[t] = a * gelu_erf(g);
                         }
                         outp[8 + j] = pack_half2(o[0], o[1]);
@@ -275,9 +317,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     tmem_ld_32x32(t_row + c * 32, r);
                     tc_wait_ld();
                     const float* sb = s_bias + c * 32;
+                    const float* sc = s_c1 + c * 32;
                     float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sb[j];
+                    for (int j = 0; j < 32; ++j) v[j] = ln_a * (__uint_as_float(r[j]) - ln_mu * sc[j]) + sb[j];
                     if (p.act_silu) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
@@ -295,6 +338,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                             }
                         }
                         if (c + 2 < NCH) load_res(c + 2, res[c & 1]);
+                    }
+                    if (p.stats_out != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (nacc0 + j < p.N) {
+                                row_sum += v[j];
+                                row_sq += v[j] * v[j];
+                            }
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < 16; ++j) outp[j] = pack_half2(v[2 * j], v[2 * j + 1]);
@@ -319,6 +371,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 }
                 buf ^= 1;
             }
+            if (p.stats_out != nullptr && row_valid)
+                reinterpret_cast<float2*>(p.stats_out)[(size_t)n_tile * p.stats_rows + pix] = make_float2(row_sum, row_sq);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -387,6 +441,18 @@ static int pick_block_n(int N, int epilogue, long m_tiles) {
 
 using namespace omg;
 
+extern "C" int omg_gemm_plan(int N, int epilogue, int W, int H, int B, int* block_n, int* n_tiles) {
+    OMG_CHECK(N >= 8 && W >= 1 && H >= 1 && B >= 1, "omg_gemm_plan: bad arguments");
+    int tw = 128;
+    while (tw / 2 >= W && tw > 1) tw /= 2;
+    const int th = 128 / tw;
+    const long m_tiles = (long)((W + tw - 1) / tw) * ((H + th - 1) / th) * B;
+    const int bn = pick_block_n(N, epilogue, m_tiles);
+    if (block_n) *block_n = bn;
+    if (n_tiles) *n_tiles = (N + bn - 1) / bn;
+    return 0;
+}
+
 extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     OMG_CHECK(d != nullptr, "omg_gemm: null descriptor");
@@ -433,6 +499,26 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     p.residual = static_cast<const __half*>(d->residual);
     p.residual_ld = d->residual_ld;
     p.act_silu = silu ? 1 : 0;
+    p.stats_out = static_cast<float*>(d->row_stats_out);
+    p.stats_in = static_cast<const float*>(d->row_stats_in);
+    p.stats_parts = d->row_stats_parts;
+    p.stats_rows = d->row_stats_stride > 0 ? d->row_stats_stride : (long long)W * H * B;
+    p.ln_inv_dim = d->ln_dim > 0 ? 1.0f / (float)d->ln_dim : 0.f;
+    p.ln_eps = d->ln_eps;
+    p.col_c1 = static_cast<const float*>(d->col_c1);
+    p.col_c2 = static_cast<const float*>(d->col_c2);
+    p.n_col_groups = d->n_col_groups > 0 ? d->n_col_groups : 1;
+    OMG_CHECK(p.n_col_groups <= 8, "omg_gemm: at most 8 column-vector row groups");
+    for (int i = 0; i < 8; ++i) {
+        p.col_group_end[i] = d->col_group_end[i];
+        OMG_CHECK(i + 1 >= p.n_col_groups || d->col_group_end[i] % 128 == 0,
+                  "omg_gemm: row-group boundary %lld is not a multiple of the 128-row tile", (long long)d->col_group_end[i]);
+    }
+    OMG_CHECK(!p.stats_in || (p.col_c1 && p.col_c2 && d->ln_dim > 0 && d->row_stats_parts >= 1 && !d->rowvec),
+              "omg_gemm: folded LayerNorm needs col_c1, col_c2, ln_dim, row_stats_parts and no rowvec");
+    OMG_CHECK(!p.stats_out || !geglu, "omg_gemm: row statistics cannot be emitted by the GEGLU epilogue");
+    OMG_CHECK((!p.stats_out && !p.stats_in) || (d->d.sw == d->d.C && d->d.sh == (int64_t)d->d.sw * W && d->d.sb == d->d.sh * H),
+              "omg_gemm: row statistics need a contiguous output view");
 
     for (int i = 0; i < d->n_a; ++i) {
         OMG_CHECK(d->a[i].ptr != nullptr, "omg_gemm: A view %d is null", i);

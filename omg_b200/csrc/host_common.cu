@@ -14,8 +14,8 @@ std::atomic<uint64_t> g_launches{0};
 bool pdl_enabled() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("OMG_NO_PDL");
-        v = (e && e[0] == '1') ? 0 : 1;
+        const char* e = getenv("OMG_PDL");
+        v = (e && e[0] == '1') ? 1 : 0;
     }
     return v == 1;
 }

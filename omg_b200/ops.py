@@ -35,7 +35,7 @@ def _ptr(t):
 
 
 def gemm(a_views, segs, w, N, Ktot, d_view, bias=None, rowvec=None, rowvec_ld=0, residual=None, residual_ld=0,
-         epilogue=L.EPI_NONE, block_n=0, w2=None):
+         epilogue=L.EPI_NONE, block_n=0, w2=None, stats_out=None, ln=None):
     d = L.GemmDesc()
     d.n_a = len(a_views)
     for i, v in enumerate(a_views):
@@ -55,10 +55,28 @@ def gemm(a_views, segs, w, N, Ktot, d_view, bias=None, rowvec=None, rowvec_ld=0,
     d.residual_ld = residual_ld
     d.epilogue = epilogue
     d.block_n = block_n
+    if stats_out is not None:
+        d.row_stats_out = stats_out.data_ptr()
+    if ln is not None:  # folded LayerNorm: (stats [parts, rows, 2] fp32, parts, rows per part, row offset, dim, eps, c1, c2)
+        stats, parts, stride, row0, dim, eps, c1, c2, group_ends = ln
+        d.row_stats_in = stats.data_ptr() + row0 * 8
+        d.row_stats_parts, d.row_stats_stride, d.ln_dim, d.ln_eps = parts, stride, dim, eps
+        d.col_c1, d.col_c2 = c1.data_ptr(), c2.data_ptr()
+        d.n_col_groups = len(group_ends)
+        for i, e in enumerate(group_ends):
+            d.col_group_end[i] = e
     L.check(L.load().omg_gemm(C.byref(d), _stream()), "omg_gemm")
 
 
-def linear(x, w, bias=None, residual=None, out=None, epilogue=L.EPI_NONE, extra=None, block_n=0, lora=None):
+def gemm_plan(N, epilogue, W, H=1, B=1):
+    """(block_n, n_tiles) omg_gemm will use; n_tiles = number of row-statistics partials a producer emits."""
+    bn, nt = C.c_int(0), C.c_int(0)
+    L.check(L.load().omg_gemm_plan(N, epilogue, W, H, B, C.byref(bn), C.byref(nt)), "omg_gemm_plan")
+    return bn.value, nt.value
+
+
+def linear(x, w, bias=None, residual=None, out=None, epilogue=L.EPI_NONE, extra=None, block_n=0, lora=None,
+           stats_out=None, ln=None):
     """out[M, N'] = epi(x[M,K] @ w[N, :K]^T (+ extra K-segments) + bias) + residual.
 
     `extra` = list of (tensor [M,Ki], column offset into w): further K-segments of the same weight matrix.
@@ -81,7 +99,8 @@ def linear(x, w, bias=None, residual=None, out=None, epilogue=L.EPI_NONE, extra=
         views.append(view4(t))
         segs.append((len(views) - 1, 0, 0, 0, t.shape[1], 0, 1))
     gemm(views, segs, w, N, Ktot, view4(out), bias=bias, residual=residual,
-         residual_ld=0 if residual is None else residual.stride(0), epilogue=epilogue, block_n=block_n, w2=w2)
+         residual_ld=0 if residual is None else residual.stride(0), epilogue=epilogue, block_n=block_n, w2=w2,
+         stats_out=stats_out, ln=ln)
     return out
 
 

@@ -34,6 +34,9 @@ def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
     return torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1)
 
 
+# (weight key suffix, LayerNorm) pairs whose LayerNorm is folded into the GEMM
+LN_CONSUMERS = (("attn1.qkv", "norm1"), ("attn2.q", "norm2"), ("ff1", "norm3"))
+
 # kernels executed through CUDA-graph replays (the C-ABI launch counter only sees direct launches; a capture counts
 # once there and is not executed)
 REPLAYED_LAUNCHES = [0]
@@ -116,6 +119,18 @@ class PackedUNet:
                 wi, bi = ops.pack_geglu_weight(sd[f"{b}.ff.net.0.proj.weight"], sd[f"{b}.ff.net.0.proj.bias"])
                 P[f"{b}.ff1.w"], P[f"{b}.ff1.b"] = _f16(wi, dev), _f16(bi, dev)
                 P[f"{b}.ff2.w"], P[f"{b}.ff2.b"] = _f16(sd[f"{b}.ff.net.2.weight"], dev), _f16(sd[f"{b}.ff.net.2.bias"], dev)
+                # LayerNorm folded into the consuming GEMM: W' = W diag(gamma) (fp16), c1 = row sums of the ROUNDED
+                # W' (so that the mean term cancels exactly in fp32), c2 = W beta + bias
+                for key, norm in LN_CONSUMERS:
+                    w = P[f"{b}.{key}.w"].float()
+                    gam, bet = P[f"{b}.{norm}.g"].float(), P[f"{b}.{norm}.b"].float()
+                    wl = (w * gam[None, :]).half()
+                    P[f"{b}.{key}.lnw"] = wl
+                    P[f"{b}.{key}.c1"] = wl.float().sum(dim=1).contiguous()
+                    c2 = w @ bet
+                    if f"{b}.{key}.b" in P:
+                        c2 = c2 + P[f"{b}.{key}.b"].float()
+                    P[f"{b}.{key}.c2"] = c2.contiguous()
         nb = len(boc)
         for i in range(nb - 1):
             P[f"down{i}.w"], P[f"down{i}.b"] = conv_w(f"down_blocks.{i}.downsamplers.0.conv")
@@ -180,7 +195,17 @@ class PackedUNet:
             B2 = torch.cat(rows, dim=0)
             if geglu:
                 B2, _ = ops.pack_geglu_weight(B2)
-            packed[key_out] = (_f16(torch.cat(As, dim=0), dev), _f16(B2, dev))
+            a_cat = torch.cat(As, dim=0)
+            entry = [_f16(a_cat, dev), _f16(B2, dev), None, None, None]
+            norm = next((n for k, n in LN_CONSUMERS if key_out.endswith("." + k)), None)
+            if norm is not None:  # A' = A diag(gamma); c1_A = row sums of rounded A'; c2_A = A beta
+                blk = key_out[: key_out.rfind(".transformer_blocks.")] + key_out[key_out.rfind(".transformer_blocks."):].split(".attn")[0].split(".ff1")[0]
+                gam, bet = self.p[f"{blk}.{norm}.g"].float(), self.p[f"{blk}.{norm}.b"].float()
+                a_ln = (a_cat.to(dev).float() * gam[None, :]).half()
+                entry[2] = a_ln.contiguous()
+                entry[3] = a_ln.float().sum(dim=1)
+                entry[4] = a_cat.to(dev).float() @ bet
+            packed[key_out] = tuple(entry)
 
         for name, ch, layers in self.tr_names:
             for lin in ("proj_in", "proj_out"):
@@ -235,7 +260,8 @@ class UNetRunner:
                  use_graphs: bool = True, groups: Optional[List[RowGroup]] = None):
         self.m, self.B, self.H, self.W = model, batch, H, W
         self.groups = groups or [RowGroup(0, batch, lora_key, model.ip is not None)]
-        self._b2_cache: Dict[str, torch.Tensor] = {}
+        self._b2_cache: Dict[str, object] = {}
+        self.ln_fold = True  # LayerNorm folded into the GEMM pairs (False: standalone LayerNorm kernel)
         self.dev = model.device
         self.ws: Dict[str, torch.Tensor] = {}
         self.use_graphs = use_graphs
@@ -272,33 +298,78 @@ class UNetRunner:
             self.ws[name] = t
         return t
 
-    def _lin(self, key, x2d, out, bias=None, residual=None, epilogue=L.EPI_NONE, groups=None, rows_per_item=None):
+    def fbuf(self, name, shape) -> torch.Tensor:
+        t = self.ws.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.zeros(shape, dtype=torch.float32, device=self.dev)
+            self.ws[name] = t
+        return t
+
+    def _ln_vectors(self, key, groups, n, active):
+        """c1 / c2 planes of the folded LayerNorm for every row group: the LoRA delta  s B (A' x)  is linear in the
+        raw input too, so a stream's LoRA simply shifts its plane by  B2 c1_A  /  B2 c2_A."""
+        P = self.m.p
+        sig = key + "|" + ",".join(f"{g.start}-{g.stop}:{g.lora_key}" for g in groups) + f"|{n}"
+        hit = self._b2_cache.get("ln|" + sig)
+        if hit is not None:
+            return hit
+        base = groups[0].start
+        if not active:
+            res = (P[key + ".c1"], P[key + ".c2"], [(groups[-1].stop - base) * n])
+        else:
+            lo = {id(g): e for g, e in active}
+            c1s, c2s = [], []
+            for g in groups:
+                c1, c2 = P[key + ".c1"], P[key + ".c2"]
+                e = lo.get(id(g))
+                if e is not None:
+                    c1 = c1 + e[1].float() @ e[3]
+                    c2 = c2 + e[1].float() @ e[4]
+                c1s.append(c1)
+                c2s.append(c2)
+            res = (torch.stack(c1s).contiguous(), torch.stack(c2s).contiguous(), [(g.stop - base) * n for g in groups])
+        self._b2_cache["ln|" + sig] = res
+        return res
+
+    def _lin(self, key, x2d, out, bias=None, residual=None, epilogue=L.EPI_NONE, groups=None, rows_per_item=None,
+             stats_out=None, ln=None):
         """Linear with the un-merged LoRA deltas of every row group: t[rows_g, cols_g] = x[rows_g] A_g^T (skinny
         GEMMs, the other blocks of t stay zero), then ONE GEMM over all rows whose extra K-segment is t against
-        [s B_1 | s B_2 | ...]."""
+        [s B_1 | s B_2 | ...].  ln = (row statistics, parts, channels): the input's LayerNorm is folded into this
+        GEMM (weights pre-multiplied by gamma, mean / rstd applied in the epilogue); stats_out: emit the row statistics
+        of this GEMM's output for the next folded LayerNorm."""
         P = self.m.p
         groups = self.groups if groups is None else groups
         active = [(g, self.m.lora_sets[g.lora_key][key]) for g in groups
                   if g.lora_key and key in self.m.lora_sets[g.lora_key]]
-        if not active:
-            return ops.linear(x2d, P[key + ".w"], bias=bias, residual=residual, out=out, epilogue=epilogue)
         M = x2d.shape[0]
         n = rows_per_item if rows_per_item is not None else M // (groups[-1].stop - groups[0].start)
-        r_tot = sum(a.shape[0] for _, (a, _) in active)
-        sig = ",".join(f"{g.start}-{g.stop}:{a.shape[0]}" for g, (a, _) in active)
+        w, ln_arg = P[key + ".w"], None
+        if ln is not None:
+            stats, parts, dim = ln
+            c1, c2, ends = self._ln_vectors(key, groups, n, active)
+            w, bias = P[key + ".lnw"], None
+            ln_arg = (stats, parts, M, 0, dim, 1e-5, c1, c2, ends)
+        if not active:
+            return ops.linear(x2d, w, bias=bias, residual=residual, out=out, epilogue=epilogue, stats_out=stats_out,
+                              ln=ln_arg)
+        a_idx = 2 if ln is not None else 0   # gamma-folded A for LayerNorm consumers
+        r_tot = sum(e[0].shape[0] for _, e in active)
+        sig = ",".join(f"{g.start}-{g.stop}:{e[0].shape[0]}" for g, e in active)
         t = self.zbuf(f"lora_t.{M}.{sig}", (M, r_tot))
         ck = key + "|" + sig + "|" + ",".join(g.lora_key for g, _ in active)
         b2 = self._b2_cache.get(ck)
         if b2 is None:
-            b2 = torch.cat([bm for _, (_, bm) in active], dim=1).contiguous() if len(active) > 1 else active[0][1][1]
+            b2 = torch.cat([e[1] for _, e in active], dim=1).contiguous() if len(active) > 1 else active[0][1][1]
             self._b2_cache[ck] = b2
         c0 = 0
         base = groups[0].start
-        for g, (a_cat, _) in active:
+        for g, e in active:
             r0, r1 = (g.start - base) * n, (g.stop - base) * n
-            ops.linear(x2d[r0:r1], a_cat, out=t[r0:r1, c0:c0 + a_cat.shape[0]])
-            c0 += a_cat.shape[0]
-        return ops.linear(x2d, P[key + ".w"], bias=bias, residual=residual, out=out, epilogue=epilogue, lora=(t, b2))
+            ops.linear(x2d[r0:r1], e[a_idx], out=t[r0:r1, c0:c0 + e[0].shape[0]])
+            c0 += e[0].shape[0]
+        return ops.linear(x2d, w, bias=bias, residual=residual, out=out, epilogue=epilogue, lora=(t, b2),
+                          stats_out=stats_out, ln=ln_arg)
 
     # ------------------------------------------------------------------------------------------- per-call setup
     def set_conditioning(self, timesteps, ctx, text_embeds: torch.Tensor, time_ids: torch.Tensor,
@@ -419,7 +490,15 @@ class UNetRunner:
         n = ops.groupnorm(x, P[name + ".norm.g"], P[name + ".norm.b"], 1e-6, 0, out=self.buf(f"tr.n.{ch}.{N}", (B, H, W, ch)),
                           stats_ws=self.stats_ws)
         h = self.buf(f"tr.h.{ch}.{N}", (M, ch))
-        self._lin(name + ".proj_in", n.view(M, ch), h, bias=P[name + ".proj_in.b"])
+        # LayerNorm fold: every GEMM that produces h also emits h's row statistics; the GEMMs that consume
+        # LayerNorm(h) run on raw h.  Needs 128-row-aligned stream boundaries (tiles must not straddle streams).
+        fold = self.ln_fold and (len(self.groups) == 1 or all(((g.stop - g.start) * N) % 128 == 0 for g in self.groups))
+        stats = lnS = None
+        if fold:
+            parts = ops.gemm_plan(ch, L.EPI_NONE, M)[1]
+            stats = self.fbuf(f"tr.rowstats.{ch}.{N}", (parts, M, 2))
+            lnS = (stats, parts, ch)
+        self._lin(name + ".proj_in", n.view(M, ch), h, bias=P[name + ".proj_in.b"], stats_out=stats)
         ln = self.buf(f"tr.ln.{ch}.{N}", (M, ch))
         qkv = self.buf(f"tr.qkv.{ch}.{N}", (B, N, 3 * ch))
         q = self.buf(f"tr.q.{ch}.{N}", (B, N, ch))
@@ -428,14 +507,18 @@ class UNetRunner:
         self_replace = variant.get("self_replace", False) and N <= variant.get("self_threshold", 0)
         ident = [(b, b, b, b) for b in range(B)]
         self_items = variant["self_items"] if self_replace else ident
+
+        def normed(b, norm):  # unfused path: materialise LayerNorm(h)
+            if fold:
+                return h
+            return ops.layernorm(h, P[f"{b}.{norm}.g"], P[f"{b}.{norm}.b"], out=ln)
+
         for k in range(layers):
             b = f"{name}.transformer_blocks.{k}"
-            ops.layernorm(h, P[b + ".norm1.g"], P[b + ".norm1.b"], out=ln)
-            self._lin(b + ".attn1.qkv", ln, qkv.view(M, 3 * ch))
+            self._lin(b + ".attn1.qkv", normed(b, "norm1"), qkv.view(M, 3 * ch), ln=lnS)
             ops.attention(qkv, qkv, qkv, o, heads, N, N, self_items, 0, ch, 2 * ch, scale=scale)
-            self._lin(b + ".attn1.out", o.view(M, ch), h, bias=P[b + ".attn1.out.b"], residual=h)
-            ops.layernorm(h, P[b + ".norm2.g"], P[b + ".norm2.b"], out=ln)
-            self._lin(b + ".attn2.q", ln, q.view(M, ch))
+            self._lin(b + ".attn1.out", o.view(M, ch), h, bias=P[b + ".attn1.out.b"], residual=h, stats_out=stats)
+            self._lin(b + ".attn2.q", normed(b, "norm2"), q.view(M, ch), ln=lnS)
             kv = self.kv[b]
             for ti, (items, wgt) in enumerate(zip(variant["cross_items"], variant["cross_weights"])):
                 ops.attention(q, kv, kv, o, heads, N, self.ctx_len, items, 0, 0, ch, scale=scale, out_weight=wgt,
@@ -444,10 +527,9 @@ class UNetRunner:
                 kvi = self.kv_ip[b]
                 ops.attention(q, kvi, kvi, o, heads, N, m.ip_tokens, variant["ip_items"], 0, 0, ch, scale=scale,
                               out_weight=m.ip_scale, accumulate=True)
-            self._lin(b + ".attn2.out", o.view(M, ch), h, bias=P[b + ".attn2.out.b"], residual=h)
-            ops.layernorm(h, P[b + ".norm3.g"], P[b + ".norm3.b"], out=ln)
-            self._lin(b + ".ff1", ln, g, bias=P[b + ".ff1.b"], epilogue=L.EPI_GEGLU)
-            self._lin(b + ".ff2", g, h, bias=P[b + ".ff2.b"], residual=h)
+            self._lin(b + ".attn2.out", o.view(M, ch), h, bias=P[b + ".attn2.out.b"], residual=h, stats_out=stats)
+            self._lin(b + ".ff1", normed(b, "norm3"), g, bias=P[b + ".ff1.b"], epilogue=L.EPI_GEGLU, ln=lnS)
+            self._lin(b + ".ff2", g, h, bias=P[b + ".ff2.b"], residual=h, stats_out=stats)
         out = self.buf(name + ".out", (B, H, W, ch))
         self._lin(name + ".proj_out", h, out.view(M, ch), bias=P[name + ".proj_out.b"], residual=x.view(M, ch))
         return out

@@ -244,3 +244,33 @@ def test_ctx_mix(ops):
     out = ops.ctx_mix(ctx, coef)
     ref = torch.einsum("wn,bnc->bwc", coef, ctx.float())
     assert rel(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("M,C,N,geglu", [(4096, 1280, 3840, False), (2048, 640, 640, False), (1024, 640, 5120, True),
+                                         (300, 320, 320, False)])
+def test_layernorm_folded_into_gemm_pair(ops, M, C, N, geglu):
+    """producer GEMM (residual add) emits row statistics; consumer GEMM applies LayerNorm in its epilogue."""
+    from omg_b200 import _lib as L
+    o, wo, bo = rnd(M, C, seed=1), rnd(C, C, scale=C ** -0.5, seed=2), rnd(C, seed=3)
+    h0 = rnd(M, C, seed=4) * 2 + 0.7                        # residual stream with a non-zero mean
+    gam, bet = rnd(C, seed=5) * 0.2 + 1, rnd(C, seed=6) * 0.3
+    w, b = rnd(N, C, scale=C ** -0.5, seed=7), rnd(N, seed=8)
+    parts = ops.gemm_plan(C, L.EPI_NONE, M)[1]
+    stats = torch.zeros(parts, M, 2, device="cuda")
+    h = h0.clone()
+    ops.linear(o, wo, bias=bo, residual=h, out=h, stats_out=stats)
+    href = o.float() @ wo.float().t() + bo.float() + h0.float()
+    assert rel(h, href) < 2e-3
+    s = stats.sum(0)
+    assert torch.allclose(s[:, 0], href.sum(1), rtol=2e-3, atol=2e-2)
+    if geglu:
+        w, b = ops.pack_geglu_weight(w, b)
+    wl = (w.float() * gam.float()[None, :]).half()
+    c1 = wl.float().sum(1).contiguous()
+    c2 = (w.float() @ bet.float() + b.float()).contiguous()
+    out = ops.linear(h, wl, epilogue=1 if geglu else 0, ln=(stats, parts, M, 0, C, 1e-5, c1, c2, [M]))
+    x = F.layer_norm(h.float(), (C,), gam.float(), bet.float(), 1e-5)
+    y = x @ w.float().t() + b.float()
+    if geglu:
+        y = y[:, 0::2] * F.gelu(y[:, 1::2])
+    assert rel(out, y) < 3e-3
