@@ -83,13 +83,14 @@ typedef struct {
      * are [n_col_groups][N] and rows [col_group_end[g-1], col_group_end[g]) use plane g (boundaries % 128 == 0). */
     int32_t n_col_groups;
     int64_t col_group_end[8];
+    int32_t cta_pair;   /* 0 = auto, 1 = single-CTA tiles, 2 = CTA pairs (cta_group::2, 256 x 256 tiles; block_n 256 only) */
 } omg_gemm_desc;
 
 int omg_gemm(const omg_gemm_desc* desc, void* stream);
 
-/* Tile plan omg_gemm will use for an output grid (W, H, B) with N channels: block_n and the number of n-tiles
- * (= row_stats_parts for a consumer of this GEMM's row statistics). */
-int omg_gemm_plan(int N, int epilogue, int W, int H, int B, int* block_n, int* n_tiles);
+/* Tile plan omg_gemm will use for an output grid (W, H, B) with N channels: block_n and the number of row-statistics
+ * partial planes this GEMM emits (= row_stats_parts for the consumer; two per n-tile). */
+int omg_gemm_plan(int N, int epilogue, int W, int H, int B, int* block_n, int* stats_parts);
 
 #define OMG_ATTN_MAX_ITEMS 16
 

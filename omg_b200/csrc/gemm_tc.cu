@@ -6,9 +6,10 @@
 //   through TMA at shifted pixel coordinates (hardware zero-fill = padding); no im2col buffer exists.
 //   Stride-2 convs and nearest-2x-upsample convs use strided "phase" views of the tensor as A / D maps.
 //   A ResBlock's 1x1 shortcut and a LoRA delta  s*B(Ax)  are just more K-segments of the same accumulator.
-// * One CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (single thread) + TMEM
-//   owner, warps 2..5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store).  Two TMEM accumulator
-//   stages so the epilogue of tile i overlaps the mainloop of tile i+1.
+// * One CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (single thread) + TMEM
+//   owner, warps 2..9 = epilogue (TMEM -> registers -> swizzled smem -> TMA store).  Two TMEM accumulator
+//   stages so the epilogue of tile i overlaps the mainloop of tile i+1.  Large GEMMs run as CTA pairs
+//   (cta_group::2, 256 x 256 tiles, each CTA stages half of the weight tile).
 // * Tile 128 (pixels) x BN (channels) x 64 (K); operands land in smem in the 128B-swizzled K-major layout
 //   the UMMA descriptors expect.
 //
@@ -26,8 +27,8 @@ namespace omg {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
-constexpr int STAGING_BYTES = 4 * 2 * 2048;  // 4 epilogue warps x double buffer x (32 rows x 64 B)
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int STAGING_BYTES = 8 * 2048;  // 8 epilogue warps x (32 rows x 64 B)
 
 struct SegDev {
     int a_map, dx, dy, a_c0, k_blocks, b_k0, b_map;
@@ -42,7 +43,7 @@ struct alignas(64) GemmParams {
     int m_tiles, n_tiles;
     int tw, th, tiles_w, tiles_h;
     int store_w, store_h;
-    int img_w, img_h;
+    int img_w, img_h, img_b;
     int N, N_out;
     const __half* bias;
     const __half* rowvec;
@@ -63,10 +64,13 @@ struct alignas(64) GemmParams {
     long long col_group_end[8];
 };
 
-template <int BN>
+// CTAS = 2: a CTA pair (cluster of 2, cta_group::2) works on a 256 x BN tile; each CTA stages its own 128 A rows and
+// HALF of the B tile, so the L2 -> smem traffic per flop drops by a third (the mainloop is TMA-latency bound: ncu shows
+// lts/xbar at ~50 % with the tensor pipe at 62 % for the 128 x 256 single-CTA tile).
+template <int BN, int CTAS = 1>
 struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = (BN / CTAS) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - STAGING_BYTES - 2 * 256 * 4 /*bias, c1*/ - 256 /*bars*/;
     static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
@@ -78,9 +82,9 @@ struct GemmCfg {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CTAS>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -95,7 +99,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    // work unit = (group of CTAS consecutive m-tiles, n-tile); CTA `cta_rank` of the pair owns m-tile unit_m*CTAS+rank
+    const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int total_tiles = ((p.m_tiles + CTAS - 1) / CTAS) * p.n_tiles;
+    const int unit0 = blockIdx.x / CTAS, unit_step = gridDim.x / CTAS;
     const int tiles_per_img = p.tiles_w * p.tiles_h;
 
     if (warp == 0 && lane == 0) {
@@ -109,13 +117,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);
+            mbar_init(&tempty_bar[i], 8 * CTAS);  // epilogue warps of every CTA of the pair arrive on the leader's
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if (warp == 1) {
+        if constexpr (CTAS == 2) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+        else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTAS == 2) cluster_sync();
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     griddep_launch_dependents();  // the prologue above overlaps the previous kernel's tail
@@ -126,22 +138,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
-                const int b = m_tile / tiles_per_img;
+            for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+                const int m_tile = (tile / p.n_tiles) * CTAS + (int)cta_rank, n_tile = tile % p.n_tiles;
+                const int b = m_tile / tiles_per_img;  // >= img_b for the odd m-tile of the last pair: TMA zero-fills
                 const int rem = m_tile % tiles_per_img;
                 const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
-                const int n0 = n_tile * BN;
+                const int n0 = n_tile * BN + (int)cta_rank * (BN / CTAS);  // this CTA's slice of the B tile
                 for (int s = 0; s < p.n_segs; ++s) {
                     const SegDev sg = p.segs[s];
                     for (int kb = 0; kb < sg.k_blocks; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
                         uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                        tma_load_4d(a_dst, &p.a_maps[sg.a_map], &full_bar[stage], sg.a_c0 + kb * BK, w0 + sg.dx,
-                                    h0 + sg.dy, b);
-                        tma_load_2d(b_dst, &p.b_maps[sg.b_map], &full_bar[stage], sg.b_k0 + kb * BK, n0);
+                        if constexpr (CTAS == 2) {
+                            // both CTAs' bytes are counted on the leader's barrier
+                            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                            tma_load_4d_pair(a_dst, &p.a_maps[sg.a_map], &full_bar[stage], sg.a_c0 + kb * BK,
+                                             w0 + sg.dx, h0 + sg.dy, b);
+                            tma_load_2d_pair(b_dst, &p.b_maps[sg.b_map], &full_bar[stage], sg.b_k0 + kb * BK, n0);
+                        } else {
+                            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                            tma_load_4d(a_dst, &p.a_maps[sg.a_map], &full_bar[stage], sg.a_c0 + kb * BK, w0 + sg.dx,
+                                        h0 + sg.dy, b);
+                            tma_load_2d(b_dst, &p.b_maps[sg.b_map], &full_bar[stage], sg.b_k0 + kb * BK, n0);
+                        }
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -152,13 +172,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------- MMA issuer (one thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(BM, BN, false, false);
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = umma_idesc_f16(BM * CTAS, BN, false, false);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = unit0; tile < total_tiles; tile += unit_step) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
@@ -174,17 +194,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             // +32 B per K=16 step inside the 128 B swizzle atom (start-address field is >>4)
-                            tc_mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate);
+                            if constexpr (CTAS == 2) tc_mma_f16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate);
+                            else tc_mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate);
                             accumulate = 1;
                         }
-                        tc_commit(&empty_bar[stage]);
+                        if constexpr (CTAS == 2) tc_commit_pair(&empty_bar[stage]);
+                        else tc_commit(&empty_bar[stage]);
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
                 }
-                tc_commit(&tfull_bar[acc]);
+                if constexpr (CTAS == 2) tc_commit_pair(&tfull_bar[acc]);
+                else tc_commit(&tfull_bar[acc]);
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -193,21 +216,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
     } else {
         // ------------------------------------------------------------- epilogue warps
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        // 8 warps: TMEM lane quarter q = warp % 4 (hardware rule), and within a quarter the two warps split the
+        // tile's 32-column chunks by parity.  (With 4 warps the epilogue of short-K tiles - K <= 1280 at BN 160 - took
+        // as long as their mainloop and throttled the tensor core through the 2-stage accumulator ring.)
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
         const int et = q * 32 + lane;  // row of the tile owned by this thread
-        uint8_t* my_stage = staging + q * 4096;
-        int buf = 0;
+        uint8_t* sbuf = staging + (q * 2 + half) * 2048;
         int acc = 0;
         uint32_t acc_phase = 0;
         constexpr int ACC_PER_CHUNK = (EPI == OMG_EPI_GEGLU) ? 64 : 32;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
+        constexpr int NCH = BN / ACC_PER_CHUNK;
+        constexpr int NIT = (NCH + 1) / 2;  // chunks per warp
+        for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+            const int m_tile = (tile / p.n_tiles) * CTAS + (int)cta_rank, n_tile = tile % p.n_tiles;
             const int b = m_tile / tiles_per_img;
             const int rem = m_tile % tiles_per_img;
             const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
             const int n0 = n_tile * BN;
 
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's s_bias readers are done
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's s_bias readers are done
             const bool ln = p.stats_in != nullptr;
             // tiles never straddle row groups (host guarantees 128-row alignment): pick this tile's c1/c2 plane
             size_t cg = 0;
@@ -217,7 +246,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     if (tile_pix0 >= p.col_group_end[g2]) cg = g2 + 1;
                 cg *= (size_t)p.N;
             }
-            for (int j = et; j < BN; j += 128) {
+            for (int j = ew * 32 + lane; j < BN; j += 256) {
                 float v = 0.f, c1 = 0.f;
                 const int n = n0 + j;
                 if (n < p.N) {
@@ -226,20 +255,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                         c1 = p.col_c1[cg + n];
                     } else {
                         if (p.bias) v += __half2float(p.bias[n]);
-                        if (p.rowvec) v += __half2float(p.rowvec[(size_t)b * p.rowvec_ld + n]);
+                        if (p.rowvec && b < p.img_b) v += __half2float(p.rowvec[(size_t)b * p.rowvec_ld + n]);
                     }
                 }
                 s_bias[j] = v;
                 s_c1[j] = c1;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
 
             const int ph = h0 + et / p.tw, pw = w0 + et % p.tw;
-            const bool row_valid = (ph < p.img_h) && (pw < p.img_w);
+            const bool row_valid = (ph < p.img_h) && (pw < p.img_w) && (b < p.img_b);
             const size_t pix = ((size_t)b * p.img_h + ph) * p.img_w + pw;
-            // folded LayerNorm: this row's mean / rstd from the producer's per-n-tile partial sums (one row per
-            // thread, so no cross-thread reduction is needed); out = rstd * (acc - mean * c1) + c2
-            float ln_a = 1.0f, ln_mu = 0.f;  // value = ln_a * (acc - ln_mu * c1) + c2
+            // folded LayerNorm: this row's mean / rstd from the producer's partial sums (one row per thread, so no
+            // cross-thread reduction is needed); out = ln_a * acc + (ln_k * c1 + c2), ln_k = -rstd * mean
+            float ln_a = 1.0f, ln_k = 0.f;
             if (ln && row_valid) {
                 float sa = 0.f, sq = 0.f;
                 for (int t = 0; t < p.stats_parts; ++t) {
@@ -247,29 +276,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     sa += st.x;
                     sq += st.y;
                 }
-                ln_mu = sa * p.ln_inv_dim;
-                ln_a = rsqrtf(fmaxf(sq * p.ln_inv_dim - ln_mu * ln_mu, 0.f) + p.ln_eps);
+                const float mu = sa * p.ln_inv_dim;
+                ln_a = rsqrtf(fmaxf(sq * p.ln_inv_dim - mu * mu, 0.f) + p.ln_eps);
+                ln_k = -ln_a * mu;
             }
-            float row_sum = 0.f, row_sq = 0.f;  // statistics of THIS GEMM's output row (stats_out)
+            float row_sum = 0.f, row_sq = 0.f;  // statistics of THIS GEMM's output row (stats_out), this warp's chunks
             // pixel origin of this warp's 32-row store box
             const int sh = h0 + (q * 32) / p.tw, sw = w0 + (q * 32) % p.tw;
 
-            // residual rows are fetched two chunks ahead (the first two before the accumulator is even ready), so
-            // their HBM/L2 latency hides behind the mainloop / the previous chunks instead of stalling each chunk
-            constexpr int NCH = BN / ACC_PER_CHUNK;
+            // residual rows are fetched two of this warp's chunks ahead (the first two before the accumulator is even
+            // ready), so their HBM/L2 latency hides behind the mainloop / the previous chunks
             uint4 res[2][4];
             const bool has_res = (EPI != OMG_EPI_GEGLU) && p.residual != nullptr && row_valid;
             const __half* res_row = has_res ? p.residual + pix * (size_t)p.residual_ld + n0 : nullptr;
             auto load_res = [&](int c, uint4(&dst)[4]) {
-                if (has_res && n0 + c * 32 < p.N) {
+                if (has_res && c < NCH && n0 + c * 32 < p.N) {
                     const uint4* rp = reinterpret_cast<const uint4*>(res_row + c * 32);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) dst[j] = __ldg(rp + j);
                 }
             };
             if constexpr (EPI != OMG_EPI_GEGLU) {
-                load_res(0, res[0]);
-                if (NCH > 1) load_res(1, res[1]);
+                load_res(half, res[0]);
+                load_res(half + 2, res[1]);
             }
 
             mbar_wait(&tfull_bar[acc], acc_phase);
@@ -277,7 +306,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             const uint32_t t_row = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
 
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) {
+            for (int it = 0; it < NIT; ++it) {
+                const int c = 2 * it + half;
+                if (c >= NCH) break;
                 const int nacc0 = n0 + c * ACC_PER_CHUNK;
                 if (nacc0 >= p.N) break;
                 uint32_t outp[16];
@@ -288,39 +319,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     tc_wait_ld();
                     const float* sb = s_bias + c * 64;
                     const float* sc = s_c1 + c * 64;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float o[2];
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            const int i = 4 * j + 2 * t;  // column of the (value, gate) pair
-                            const float a = ln_a * (__uint_as_float(r0[i]) - ln_mu * sc[i]) + sb[i];
-                            const float g = ln_a * (__uint_as_float(r0[i + 1]) - ln_mu * sc[i + 1]) + sb[i + 1];
-                            o[t] = a * gelu_erf(g);
+                    auto pair_out = [&](const uint32_t(&r)[32], int off, int i) {
+                        float a, g;
+                        if (ln) {
+                            a = fmaf(ln_a, __uint_as_float(r[i]), fmaf(ln_k, sc[off + i], sb[off + i]));
+                            g = fmaf(ln_a, __uint_as_float(r[i + 1]), fmaf(ln_k, sc[off + i + 1], sb[off + i + 1]));
+                        } else {
+                            a = __uint_as_float(r[i]) + sb[off + i];
+                            g = __uint_as_float(r[i + 1]) + sb[off + i + 1];
                         }
-                        outp[j] = pack_half2(o[0], o[1]);
-                    }
+                        return a * gelu_erf(g);
+                    };
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float o[2];
+                    for (int j = 0; j < 8; ++j)  // columns (4j, 4j+1) and (4j+2, 4j+3) are (value, gate) pairs
+                        outp[j] = pack_half2(pair_out(r0, 0, 4 * j), pair_out(r0, 0, 4 * j + 2));
 #pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            const int i = 4 * j + 2 * t;
-                            const float a = ln_a * (__uint_as_float(r1[i]) - ln_mu * sc[32 + i]) + sb[32 + i];
-                            const float g = ln_a * (__uint_as_float(r1[i + 1]) - ln_mu * sc[32 + i + 1]) + sb[32 + i + 1];
-                            o[t] = a * gelu_erf(g);
-                        }
-                        outp[8 + j] = pack_half2(o[0], o[1]);
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        outp[8 + j] = pack_half2(pair_out(r1, 32, 4 * j), pair_out(r1, 32, 4 * j + 2));
                 } else {
                     uint32_t r[32];
                     tmem_ld_32x32(t_row + c * 32, r);
                     tc_wait_ld();
                     const float* sb = s_bias + c * 32;
-                    const float* sc = s_c1 + c * 32;
                     float v[32];
+                    if (ln) {
+                        const float* sc = s_c1 + c * 32;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = ln_a * (__uint_as_float(r[j]) - ln_mu * sc[j]) + sb[j];
+                        for (int j = 0; j < 32; ++j) v[j] = fmaf(ln_a, __uint_as_float(r[j]), fmaf(ln_k, sc[j], sb[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sb[j];
+                    }
                     if (p.act_silu) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
@@ -328,7 +357,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     if (has_res) {
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
-                            const uint4 u = res[c & 1][j4];
+                            const uint4 u = res[it & 1][j4];
                             const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
@@ -337,24 +366,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                                 v[j4 * 8 + 2 * t + 1] += f.y;
                             }
                         }
-                        if (c + 2 < NCH) load_res(c + 2, res[c & 1]);
+                        load_res(c + 4, res[it & 1]);
                     }
                     if (p.stats_out != nullptr) {
+                        if (nacc0 + 32 <= p.N) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (nacc0 + j < p.N) {
+                            for (int j = 0; j < 32; ++j) {
                                 row_sum += v[j];
-                                row_sq += v[j] * v[j];
+                                row_sq = fmaf(v[j], v[j], row_sq);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (nacc0 + j < p.N) {
+                                    row_sum += v[j];
+                                    row_sq = fmaf(v[j], v[j], row_sq);
+                                }
                             }
                         }
                     }
 #pragma unroll
                     for (int j = 0; j < 16; ++j) outp[j] = pack_half2(v[2 * j], v[2 * j + 1]);
                 }
-                // staging buffer `buf` was last read by the TMA store issued two chunks ago
-                if (lane == 0) tma_store_wait_read<1>();
+                // this warp's staging buffer was last read by the TMA store of its previous chunk
+                if (lane == 0) tma_store_wait_read<0>();
                 __syncwarp();
-                uint8_t* sbuf = my_stage + buf * 2048;
                 // 64 B rows, SWIZZLE_64B: 16 B chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -369,13 +405,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     tma_store_4d(&p.d_map, sbuf, nout0, sw, sh, b);
                     tma_store_commit();
                 }
-                buf ^= 1;
             }
-            if (p.stats_out != nullptr && row_valid)
-                reinterpret_cast<float2*>(p.stats_out)[(size_t)n_tile * p.stats_rows + pix] = make_float2(row_sum, row_sq);
+            if (p.stats_out != nullptr && row_valid)  // one partial per (n-tile, chunk parity)
+                reinterpret_cast<float2*>(p.stats_out)[(size_t)(n_tile * 2 + half) * p.stats_rows + pix] =
+                    make_float2(row_sum, row_sq);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if (leader) mbar_arrive(&tempty_bar[acc]);
+                else mbar_arrive_remote(&tempty_bar[acc], 0);  // the pair's MMA issuer lives in the leader CTA
+            }
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
@@ -385,8 +424,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (CTAS == 2) {
+        cluster_sync();  // the peer may still arrive on / multicast into this CTA's barriers
+        if (warp == 1) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    } else {
+        __syncthreads();
+        if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -398,23 +442,32 @@ static int view_to_tmap(CUtensorMap* m, const omg_view4& v, uint32_t box_c, uint
     return make_tmap_f16(m, v.ptr, 4, dims, strides, box, sw);
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CTAS>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CTAS>;
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
-        OMG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        OMG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::SMEM_BYTES));
         int dev = 0;
         OMG_CUDA(cudaGetDevice(&dev));
         OMG_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         configured = true;
     }
-    const int total = p.m_tiles * p.n_tiles;
-    const int grid = std::min(total, num_sms);
-    OMG_CUDA(launch_pdl(gemm_tc_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, p));
+    const int units = ((p.m_tiles + CTAS - 1) / CTAS) * p.n_tiles;
+    const int grid = CTAS * std::min(units, num_sms / CTAS);
+    OMG_CUDA(launch_cluster(gemm_tc_kernel<BN, EPI, CTAS>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, CTAS, p));
     return check_launch("gemm_tc_kernel");
+}
+
+// CTA pairs pay off when the pair-tiles still fill the 74 SM pairs about as well as single tiles fill 148 SMs
+static bool use_cta_pair(long m_tiles, long n_tiles) {
+    if (m_tiles < 2) return false;
+    const long t1 = m_tiles * n_tiles, t2 = ((m_tiles + 1) / 2) * n_tiles;
+    const double e1 = (double)t1 / (double)(((t1 + 147) / 148) * 148);
+    const double e2 = (double)t2 / (double)(((t2 + 73) / 74) * 74);
+    return e2 * 1.12 >= e1;
 }
 
 static int pick_block_n(int N, int epilogue, long m_tiles) {
@@ -449,7 +502,7 @@ extern "C" int omg_gemm_plan(int N, int epilogue, int W, int H, int B, int* bloc
     const long m_tiles = (long)((W + tw - 1) / tw) * ((H + th - 1) / th) * B;
     const int bn = pick_block_n(N, epilogue, m_tiles);
     if (block_n) *block_n = bn;
-    if (n_tiles) *n_tiles = (N + bn - 1) / bn;
+    if (n_tiles) *n_tiles = 2 * ((N + bn - 1) / bn);  // row-statistics partials: one per (n-tile, chunk parity)
     return 0;
 }
 
@@ -486,6 +539,7 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     p.store_h = 32 / p.store_w;
     p.img_w = W;
     p.img_h = H;
+    p.img_b = B;
     p.m_tiles = p.tiles_w * p.tiles_h * B;
     p.N = d->N;
     p.N_out = N_out;
@@ -558,11 +612,27 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
         p.segs[s] = SegDev{sg.a_idx, sg.dx, sg.dy, sg.a_c0, (sg.k_len + BK - 1) / BK, sg.b_k0, sg.b_idx};
     }
 
-    if (geglu) return launch_gemm<256, OMG_EPI_GEGLU>(p, stream);
+    // the TMA box of the weight tile is this CTA's slice: BN rows, or BN/2 for a CTA pair
+    const bool pair = bn == 256 && (d->cta_pair == 2 || (d->cta_pair == 0 && use_cta_pair(p.m_tiles, p.n_tiles)));
+    if (pair) {
+        for (int i = 0; i < 2; ++i) {
+            const void* wp = i == 0 ? d->w : d->w2;
+            if (!wp) continue;
+            const int kt = i == 0 ? d->Ktot : d->K2tot;
+            const uint64_t dims[2] = {(uint64_t)kt, (uint64_t)d->N};
+            const uint64_t strides[2] = {1, (uint64_t)kt};
+            const uint32_t box[2] = {BK, 128};
+            if (make_tmap_f16(&p.b_maps[i], wp, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+        }
+        if (!d->w2) p.b_maps[1] = p.b_maps[0];
+        if (geglu) return launch_gemm<256, OMG_EPI_GEGLU, 2>(p, stream);
+        return launch_gemm<256, OMG_EPI_NONE, 2>(p, stream);
+    }
+    if (geglu) return launch_gemm<256, OMG_EPI_GEGLU, 1>(p, stream);
     switch (bn) {
-        case 64: return launch_gemm<64, OMG_EPI_NONE>(p, stream);
-        case 128: return launch_gemm<128, OMG_EPI_NONE>(p, stream);
-        case 160: return launch_gemm<160, OMG_EPI_NONE>(p, stream);
-        default: return launch_gemm<256, OMG_EPI_NONE>(p, stream);
+        case 64: return launch_gemm<64, OMG_EPI_NONE, 1>(p, stream);
+        case 128: return launch_gemm<128, OMG_EPI_NONE, 1>(p, stream);
+        case 160: return launch_gemm<160, OMG_EPI_NONE, 1>(p, stream);
+        default: return launch_gemm<256, OMG_EPI_NONE, 1>(p, stream);
     }
 }

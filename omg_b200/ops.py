@@ -35,8 +35,9 @@ def _ptr(t):
 
 
 def gemm(a_views, segs, w, N, Ktot, d_view, bias=None, rowvec=None, rowvec_ld=0, residual=None, residual_ld=0,
-         epilogue=L.EPI_NONE, block_n=0, w2=None, stats_out=None, ln=None):
+         epilogue=L.EPI_NONE, block_n=0, w2=None, stats_out=None, ln=None, cta_pair=0):
     d = L.GemmDesc()
+    d.cta_pair = cta_pair
     d.n_a = len(a_views)
     for i, v in enumerate(a_views):
         d.a[i] = v
@@ -76,7 +77,7 @@ def gemm_plan(N, epilogue, W, H=1, B=1):
 
 
 def linear(x, w, bias=None, residual=None, out=None, epilogue=L.EPI_NONE, extra=None, block_n=0, lora=None,
-           stats_out=None, ln=None):
+           stats_out=None, ln=None, cta_pair=0):
     """out[M, N'] = epi(x[M,K] @ w[N, :K]^T (+ extra K-segments) + bias) + residual.
 
     `extra` = list of (tensor [M,Ki], column offset into w): further K-segments of the same weight matrix.
@@ -100,7 +101,7 @@ def linear(x, w, bias=None, residual=None, out=None, epilogue=L.EPI_NONE, extra=
         segs.append((len(views) - 1, 0, 0, 0, t.shape[1], 0, 1))
     gemm(views, segs, w, N, Ktot, view4(out), bias=bias, residual=residual,
          residual_ld=0 if residual is None else residual.stride(0), epilogue=epilogue, block_n=block_n, w2=w2,
-         stats_out=stats_out, ln=ln)
+         stats_out=stats_out, ln=ln, cta_pair=cta_pair)
     return out
 
 
@@ -108,7 +109,7 @@ def _taps3x3(Cin, a_idx=0, c0=0, k0=0):
     return [(a_idx, kx - 1, ky - 1, c0, Cin, k0 + (ky * 3 + kx) * Cin) for ky in range(3) for kx in range(3)]
 
 
-def conv3x3(x, w, bias=None, rowvec=None, residual=None, out=None, shortcut=None, block_n=0):
+def conv3x3(x, w, bias=None, rowvec=None, residual=None, out=None, shortcut=None, block_n=0, cta_pair=0):
     """3x3 / stride 1 / pad 1 conv over (B,H,W,Cin).  w = [N, 9*Cin (+ shortcut K)] packed (ky, kx, c).
 
     shortcut = list of (tensor (B,H,W,Ci), weight column offset): 1x1-conv K-segments added to the same accumulator
@@ -125,7 +126,7 @@ def conv3x3(x, w, bias=None, rowvec=None, residual=None, out=None, shortcut=None
         segs.append((len(views) - 1, 0, 0, 0, t.shape[3], off))
     gemm(views, segs, w, N, Ktot, view4(out), bias=bias, rowvec=rowvec,
          rowvec_ld=0 if rowvec is None else rowvec.stride(0),
-         residual=residual, residual_ld=0 if residual is None else N, block_n=block_n)
+         residual=residual, residual_ld=0 if residual is None else N, block_n=block_n, cta_pair=cta_pair)
     return out
 
 

@@ -13,6 +13,7 @@ What is hoisted out of the per-step path (all step-invariant in the reference to
   * the ControlNet conditioning embedding of the (constant) condition image: once per call.
 """
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -261,7 +262,8 @@ class UNetRunner:
         self.m, self.B, self.H, self.W = model, batch, H, W
         self.groups = groups or [RowGroup(0, batch, lora_key, model.ip is not None)]
         self._b2_cache: Dict[str, object] = {}
-        self.ln_fold = True  # LayerNorm folded into the GEMM pairs (False: standalone LayerNorm kernel)
+        # LayerNorm folded into the GEMM pairs (OMG_LN_FOLD=0: standalone LayerNorm kernel)
+        self.ln_fold = os.environ.get("OMG_LN_FOLD", "1") != "0"
         self.dev = model.device
         self.ws: Dict[str, torch.Tensor] = {}
         self.use_graphs = use_graphs

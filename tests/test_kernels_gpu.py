@@ -274,3 +274,39 @@ def test_layernorm_folded_into_gemm_pair(ops, M, C, N, geglu):
     if geglu:
         y = y[:, 0::2] * F.gelu(y[:, 1::2])
     assert rel(out, y) < 3e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 3840, 1280), (2176, 512, 256), (256, 256, 64), (8192, 1280, 640), (300, 768, 320)])
+def test_linear_cta_pair(ops, M, N, K):
+    """cta_group::2: a CTA pair computes 256 x 256 tiles (odd m-tile counts and ragged M included)."""
+    x, w, b = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2), rnd(N, seed=3)
+    r = rnd(M, N, seed=4)
+    out = ops.linear(x, w, bias=b, residual=r, block_n=256, cta_pair=2)
+    ref = x.float() @ w.float().t() + b.float() + r.float()
+    assert rel(out, ref) < 2e-3
+    out1 = ops.linear(x, w, bias=b, residual=r, block_n=256, cta_pair=1)
+    assert torch.equal(out, out1)      # same accumulation order per element: bit-identical to single-CTA tiles
+
+
+def test_cta_pair_geglu_lora_conv(ops):
+    M, C = 2048, 640
+    x = rnd(M, C, seed=1)
+    w, b = rnd(8 * C, C, scale=C ** -0.5, seed=2), rnd(8 * C, seed=3)
+    wi, bi = ops.pack_geglu_weight(w, b)
+    out = ops.linear(x, wi, bias=bi, epilogue=1, cta_pair=2)
+    h = x.float() @ w.float().t() + b.float()
+    assert rel(out, h[:, :4 * C] * F.gelu(h[:, 4 * C:])) < 2e-3
+    # LoRA second weight matrix through the pair path
+    N, R = 1280, 64
+    wq, a, bw = rnd(N, C, scale=C ** -0.5, seed=4), rnd(R, C, scale=C ** -0.5, seed=5), rnd(N, R, scale=0.05, seed=6)
+    t = ops.linear(x, a)
+    out = ops.linear(x, wq, lora=(t, bw), block_n=256, cta_pair=2)
+    assert rel(out, x.float() @ wq.float().t() + t.float() @ bw.float().t()) < 2e-3
+    # conv3x3 with time-embedding row vector
+    B, H, W, Cin, Nc = 2, 32, 32, 128, 512
+    xi = rnd(B, H, W, Cin, seed=7)
+    wc = rnd(Nc, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=8)
+    bc, temb = rnd(Nc, seed=9), rnd(B, Nc, seed=10)
+    out = ops.conv3x3(xi, ops.pack_conv3x3_weight(wc), bias=bc, rowvec=temb, block_n=256, cta_pair=2)
+    ref = F.conv2d(xi.float().permute(0, 3, 1, 2), wc.float(), bc.float(), padding=1) + temb.float()[:, :, None, None]
+    assert rel(out.permute(0, 3, 1, 2), ref) < 2e-3
