@@ -462,8 +462,10 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
 }
 
 // CTA pairs pay off when the pair-tiles still fill the 74 SM pairs about as well as single tiles fill 148 SMs
-static bool use_cta_pair(long m_tiles, long n_tiles) {
-    if (m_tiles < 2) return false;
+static bool use_cta_pair(long m_tiles, long n_tiles, long k_blocks) {
+    // measured (profiles/, kernel_bench): +5..9 % for K >= 1280 (ff1/ff2/qkv at c = 1280), -8 % for K = 640 where
+    // the short mainloop cannot amortise the pair's cluster synchronisation and doubled epilogue per launch slot
+    if (m_tiles < 2 || k_blocks < 16) return false;
     const long t1 = m_tiles * n_tiles, t2 = ((m_tiles + 1) / 2) * n_tiles;
     const double e1 = (double)t1 / (double)(((t1 + 147) / 148) * 148);
     const double e2 = (double)t2 / (double)(((t2 + 73) / 74) * 74);
@@ -613,7 +615,9 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     }
 
     // the TMA box of the weight tile is this CTA's slice: BN rows, or BN/2 for a CTA pair
-    const bool pair = bn == 256 && (d->cta_pair == 2 || (d->cta_pair == 0 && use_cta_pair(p.m_tiles, p.n_tiles)));
+    long k_blocks = 0;
+    for (int i = 0; i < p.n_segs; ++i) k_blocks += p.segs[i].k_blocks;
+    const bool pair = bn == 256 && (d->cta_pair == 2 || (d->cta_pair == 0 && use_cta_pair(p.m_tiles, p.n_tiles, k_blocks)));
     if (pair) {
         for (int i = 0; i < 2; ++i) {
             const void* wp = i == 0 ? d->w : d->w2;
