@@ -31,7 +31,7 @@ class GemmDesc(C.Structure):
                 ("residual_ld", C.c_int32), ("epilogue", C.c_int32), ("block_n", C.c_int32),
                 ("row_stats_out", C.c_void_p), ("row_stats_in", C.c_void_p), ("row_stats_parts", C.c_int32),
                 ("row_stats_stride", C.c_int64), ("ln_dim", C.c_int32), ("ln_eps", C.c_float), ("col_c1", C.c_void_p), ("col_c2", C.c_void_p),
-                ("n_col_groups", C.c_int32), ("col_group_end", C.c_int64 * 8), ("cta_pair", C.c_int32)]
+                ("n_col_groups", C.c_int32), ("col_group_end", C.c_int64 * 8), ("w_group_planes", C.c_int32), ("cta_pair", C.c_int32)]
 
 
 class AttnDesc(C.Structure):

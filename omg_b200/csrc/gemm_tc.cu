@@ -62,6 +62,7 @@ struct alignas(64) GemmParams {
     const float* col_c2;       // [N] fp32: W beta + bias
     int n_col_groups;          // c1/c2 are [n_col_groups][N]; row group g = rows [col_group_end[g-1], col_group_end[g])
     long long col_group_end[8];
+    int w_group_rows;          // > 0: the weight matrix holds one [N, K] plane per row group (per-stream merged LoRA)
 };
 
 // CTAS = 2: a CTA pair (cluster of 2, cta_group::2) works on a 256 x BN tile; each CTA stages its own 128 A rows and
@@ -143,7 +144,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 const int b = m_tile / tiles_per_img;  // >= img_b for the odd m-tile of the last pair: TMA zero-fills
                 const int rem = m_tile % tiles_per_img;
                 const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
-                const int n0 = n_tile * BN + (int)cta_rank * (BN / CTAS);  // this CTA's slice of the B tile
+                int n0 = n_tile * BN + (int)cta_rank * (BN / CTAS);  // this CTA's slice of the B tile
+                if (p.w_group_rows > 0) {  // multi-stream launch: this tile's stream selects the weight plane
+                    const long long tile_pix0 = ((long long)b * p.img_h + h0) * p.img_w + w0;
+                    for (int g2 = 0; g2 + 1 < p.n_col_groups; ++g2)
+                        if (tile_pix0 >= p.col_group_end[g2]) n0 += p.w_group_rows;
+                }
                 for (int s = 0; s < p.n_segs; ++s) {
                     const SegDev sg = p.segs[s];
                     for (int kb = 0; kb < sg.k_blocks; ++kb) {
@@ -564,6 +570,8 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     p.col_c1 = static_cast<const float*>(d->col_c1);
     p.col_c2 = static_cast<const float*>(d->col_c2);
     p.n_col_groups = d->n_col_groups > 0 ? d->n_col_groups : 1;
+    p.w_group_rows = d->w_group_planes > 0 ? d->N : 0;
+    OMG_CHECK(d->w_group_planes == 0 || d->w_group_planes == p.n_col_groups, "omg_gemm: w_group_planes must equal n_col_groups");
     OMG_CHECK(p.n_col_groups <= 8, "omg_gemm: at most 8 column-vector row groups");
     for (int i = 0; i < 8; ++i) {
         p.col_group_end[i] = d->col_group_end[i];
@@ -582,7 +590,8 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     }
     for (int i = d->n_a; i < OMG_MAX_A; ++i) p.a_maps[i] = p.a_maps[0];
     {
-        const uint64_t dims[2] = {(uint64_t)d->Ktot, (uint64_t)d->N};
+        const uint64_t planes = d->w_group_planes > 0 ? (uint64_t)d->w_group_planes : 1;
+        const uint64_t dims[2] = {(uint64_t)d->Ktot, (uint64_t)d->N * planes};
         const uint64_t strides[2] = {1, (uint64_t)d->Ktot};
         const uint32_t box[2] = {BK, (uint32_t)bn};
         if (make_tmap_f16(&p.b_maps[0], d->w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
@@ -617,13 +626,17 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     // the TMA box of the weight tile is this CTA's slice: BN rows, or BN/2 for a CTA pair
     long k_blocks = 0;
     for (int i = 0; i < p.n_segs; ++i) k_blocks += p.segs[i].k_blocks;
-    const bool pair = bn == 256 && (d->cta_pair == 2 || (d->cta_pair == 0 && use_cta_pair(p.m_tiles, p.n_tiles, k_blocks)));
+    bool pair_ok = true;  // both CTAs of a pair must belong to the same stream
+    for (int i = 0; i + 1 < p.n_col_groups; ++i) pair_ok = pair_ok && (p.col_group_end[i] % 256 == 0);
+    const bool pair = bn == 256 && pair_ok &&
+                      (d->cta_pair == 2 || (d->cta_pair == 0 && use_cta_pair(p.m_tiles, p.n_tiles, k_blocks)));
     if (pair) {
         for (int i = 0; i < 2; ++i) {
             const void* wp = i == 0 ? d->w : d->w2;
             if (!wp) continue;
             const int kt = i == 0 ? d->Ktot : d->K2tot;
-            const uint64_t dims[2] = {(uint64_t)kt, (uint64_t)d->N};
+            const uint64_t planes = (i == 0 && d->w_group_planes > 0) ? (uint64_t)d->w_group_planes : 1;
+            const uint64_t dims[2] = {(uint64_t)kt, (uint64_t)d->N * planes};
             const uint64_t strides[2] = {1, (uint64_t)kt};
             const uint32_t box[2] = {BK, 128};
             if (make_tmap_f16(&p.b_maps[i], wp, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;

@@ -35,9 +35,13 @@ def _ptr(t):
 
 
 def gemm(a_views, segs, w, N, Ktot, d_view, bias=None, rowvec=None, rowvec_ld=0, residual=None, residual_ld=0,
-         epilogue=L.EPI_NONE, block_n=0, w2=None, stats_out=None, ln=None, cta_pair=0):
+         epilogue=L.EPI_NONE, block_n=0, w2=None, stats_out=None, ln=None, cta_pair=0, row_groups=None):
     d = L.GemmDesc()
     d.cta_pair = cta_pair
+    if row_groups is not None:  # per-stream weight planes: w is [len(row_groups) * N, Ktot]
+        d.w_group_planes = d.n_col_groups = len(row_groups)
+        for i, e in enumerate(row_groups):
+            d.col_group_end[i] = e
     d.n_a = len(a_views)
     for i, v in enumerate(a_views):
         d.a[i] = v
@@ -77,7 +81,7 @@ def gemm_plan(N, epilogue, W, H=1, B=1):
 
 
 def linear(x, w, bias=None, residual=None, out=None, epilogue=L.EPI_NONE, extra=None, block_n=0, lora=None,
-           stats_out=None, ln=None, cta_pair=0):
+           stats_out=None, ln=None, cta_pair=0, row_groups=None):
     """out[M, N'] = epi(x[M,K] @ w[N, :K]^T (+ extra K-segments) + bias) + residual.
 
     `extra` = list of (tensor [M,Ki], column offset into w): further K-segments of the same weight matrix.
@@ -86,6 +90,8 @@ def linear(x, w, bias=None, residual=None, out=None, epilogue=L.EPI_NONE, extra=
     _chk16(x)
     M, K = x.shape
     N, Ktot = w.shape
+    if row_groups is not None:
+        N //= len(row_groups)
     n_out = N // 2 if epilogue == L.EPI_GEGLU else N
     if out is None:
         out = torch.empty((M, n_out), dtype=torch.float16, device=x.device)
@@ -101,7 +107,7 @@ def linear(x, w, bias=None, residual=None, out=None, epilogue=L.EPI_NONE, extra=
         segs.append((len(views) - 1, 0, 0, 0, t.shape[1], 0, 1))
     gemm(views, segs, w, N, Ktot, view4(out), bias=bias, residual=residual,
          residual_ld=0 if residual is None else residual.stride(0), epilogue=epilogue, block_n=block_n, w2=w2,
-         stats_out=stats_out, ln=ln, cta_pair=cta_pair)
+         stats_out=stats_out, ln=ln, cta_pair=cta_pair, row_groups=row_groups)
     return out
 
 

@@ -264,6 +264,8 @@ class UNetRunner:
         self._b2_cache: Dict[str, object] = {}
         # LayerNorm folded into the GEMM pairs (OMG_LN_FOLD=0: standalone LayerNorm kernel)
         self.ln_fold = os.environ.get("OMG_LN_FOLD", "1") != "0"
+        # LoRA streams of a grouped launch use per-stream merged weight planes (OMG_LORA=unmerged: K-segment path)
+        self.merge_lora = os.environ.get("OMG_LORA", "merged") != "unmerged"
         self.dev = model.device
         self.ws: Dict[str, torch.Tensor] = {}
         self.use_graphs = use_graphs
@@ -333,6 +335,40 @@ class UNetRunner:
         self._b2_cache["ln|" + sig] = res
         return res
 
+    def _merged_planes(self, key, groups, active, folded):
+        """[G*N, K] fp16 stack of per-stream weights (W, or W + s B_g A_g for LoRA streams) and, for LayerNorm
+        consumers, the matching c1/c2 planes (gamma folded AFTER the merge, c1 from the rounded weights)."""
+        P = self.m.p
+        ck = "merged|" + key + "|" + ",".join(f"{g.start}-{g.stop}:{g.lora_key}" for g in groups) + f"|{folded}"
+        hit = self._b2_cache.get(ck)
+        if hit is not None:
+            return hit
+        lo = {id(g): e for g, e in active}
+        w = P[key + ".w"].float()
+        gam = bet = None
+        if folded:
+            norm = next(nm for k, nm in LN_CONSUMERS if key.endswith("." + k))
+            blk = key[: -(len(next(k for k, nm in LN_CONSUMERS if key.endswith("." + k))) + 1)]
+            gam, bet = P[f"{blk}.{norm}.g"].float(), P[f"{blk}.{norm}.b"].float()
+        ws, c1s, c2s = [], [], []
+        for g in groups:
+            e = lo.get(id(g))
+            wg = w if e is None else w + e[1].float() @ e[0].float()
+            if folded:
+                wl = (wg * gam[None, :]).half()
+                c2 = wg @ bet
+                if (key + ".b") in P:
+                    c2 = c2 + P[key + ".b"].float()
+                ws.append(wl)
+                c1s.append(wl.float().sum(dim=1))
+                c2s.append(c2)
+            else:
+                ws.append(wg.half())
+        res = (torch.cat(ws, dim=0).contiguous(), torch.stack(c1s).contiguous() if folded else None,
+               torch.stack(c2s).contiguous() if folded else None)
+        self._b2_cache[ck] = res
+        return res
+
     def _lin(self, key, x2d, out, bias=None, residual=None, epilogue=L.EPI_NONE, groups=None, rows_per_item=None,
              stats_out=None, ln=None):
         """Linear with the un-merged LoRA deltas of every row group: t[rows_g, cols_g] = x[rows_g] A_g^T (skinny
@@ -355,6 +391,16 @@ class UNetRunner:
         if not active:
             return ops.linear(x2d, w, bias=bias, residual=residual, out=out, epilogue=epilogue, stats_out=stats_out,
                               ln=ln_arg)
+        base = groups[0].start
+        ends = [(g.stop - base) * n for g in groups]
+        if self.merge_lora and groups is self.groups and len(groups) <= 8 and all(e % 128 == 0 for e in ends[:-1]):
+            # per-stream weight planes W_g = W + s B_g A_g (built once, resident in HBM): the grouped launch picks the
+            # plane of the stream a tile belongs to, so the per-step path has no LoRA GEMMs or K-segments at all
+            wm, c1m, c2m = self._merged_planes(key, groups, active, ln is not None)
+            if ln is not None:
+                ln_arg = (ln[0], ln[1], M, 0, ln[2], 1e-5, c1m, c2m, ends)
+            return ops.linear(x2d, wm, bias=bias, residual=residual, out=out, epilogue=epilogue, stats_out=stats_out,
+                              ln=ln_arg, row_groups=ends)
         a_idx = 2 if ln is not None else 0   # gamma-folded A for LayerNorm consumers
         r_tot = sum(e[0].shape[0] for _, e in active)
         sig = ",".join(f"{g.start}-{g.stop}:{e[0].shape[0]}" for g, e in active)

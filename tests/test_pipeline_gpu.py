@@ -22,8 +22,8 @@ def _masks(size):
     return m1, m2
 
 
-@pytest.mark.parametrize("share", [False, True])
-def test_lora_two_stage_pipeline(share):
+@pytest.mark.parametrize("share,lora_mode", [(False, "merged"), (True, "merged"), (True, "unmerged")])
+def test_lora_two_stage_pipeline(share, lora_mode, monkeypatch):
     """share=True: the concept UNet is the main UNet's packed weights -> fusion steps run as ONE grouped forward
     (main rows + both concepts' rows); share=False: separate concept forwards."""
     from omg_b200.config import UNetConfig
@@ -33,6 +33,7 @@ def test_lora_two_stage_pipeline(share):
     from oracle import p2p as op2p
     from oracle import unet as ou
     from oracle.pipeline import Concept, denoise
+    monkeypatch.setenv("OMG_LORA", lora_mode)
     cfg = UNetConfig.tiny()
     sd = weights(cfg, 0)
     size = 256

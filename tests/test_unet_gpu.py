@@ -147,16 +147,18 @@ def test_concept_unet_lora(env):
     la, ls = lora(cfg, 11), lora(cfg, 12)
     model = PackedUNet(cfg, env["sd"])
     model.add_lora_set("c", [(la, 0.7), (ls, 0.5)], 0.8)
-    r = UNetRunner(model, B, H, W, lora_key="c", use_graphs=False)
-    r.set_conditioning([250.0], ctx, pooled, tid)
-    r.sample_in.copy_(to_nhwc8(x))
-    out = from_nhwc(r.forward(0))
     c = ou.Ctx(env["sd"], ocfg(cfg), lora=oracle_lora([(la, 0.7), (ls, 0.5)], 0.8))
     ref = ou.unet_forward(c, x, 250.0, ctx, pooled, tid)
     base = ou.unet_forward(ou.Ctx(env["sd"], ocfg(cfg)), x, 250.0, ctx, pooled, tid)
-    e = rel(out, ref)
-    print("lora unet rel err", e, "lora effect", rel(ref, base))
-    assert e < TOL and rel(ref, base) > 5 * e
+    for merged in (True, False):   # per-stream merged weight planes / un-merged K-segment path
+        r = UNetRunner(model, B, H, W, lora_key="c", use_graphs=False)
+        r.merge_lora = merged
+        r.set_conditioning([250.0], ctx, pooled, tid)
+        r.sample_in.copy_(to_nhwc8(x))
+        out = from_nhwc(r.forward(0))
+        e = rel(out, ref)
+        print("lora unet rel err", e, "merged" if merged else "unmerged", "lora effect", rel(ref, base))
+        assert e < TOL and rel(ref, base) > 5 * e
 
 
 def test_controlnet_and_residuals(env):
