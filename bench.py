@@ -134,7 +134,7 @@ def run_reference(args, rank, world):
     here, so this is the fp32 oracle port timed on the host cores; each step = one UNet sample-forward at the
     workload's latent size (a bounded sample of the 296 an image needs)."""
     if rank != 0:
-        return
+        return None
     from omg_b200.config import UNetConfig
     cfg = UNetConfig.sdxl()
     threads = host_threads()
@@ -149,14 +149,14 @@ def run_reference(args, rank, world):
     value = 1.0 / (SAMPLE_FORWARDS_PER_IMAGE * per)
     sample = (f"{args.steps} x one fp32 UNet sample-forward at 128x128 latents (6.76 TFLOP each) on {threads} host "
               f"threads; images/s extrapolated as 1/(296 x {per:.2f} s)")
-    print(json.dumps({
+    return json.dumps({
         "impl": "reference", "metric": "1024^2 images/sec @30 steps, 2 concepts", "value": value,
         "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": "images/sec", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def workload_config(n_gpus):
@@ -168,7 +168,30 @@ def workload_config(n_gpus):
             "l2_policy": "inputs+weights (5.1 GB) exceed the 126 MB L2; no flush needed between steps"}
 
 
+class StdoutToStderr:
+    """The driver parses ONE JSON line from stdout: libraries (NCCL's version banner, pipeline prints) write to fd 1 too,
+    so everything except the final line is routed to stderr at the file-descriptor level."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def main():
+    with StdoutToStderr():
+        line = _main()
+    if line is not None:
+        print(line, flush=True)
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
@@ -181,6 +204,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    result = None
 
     import torch.distributed as dist
     from omg_b200 import _lib, factory, ops, synthetic
@@ -265,6 +289,10 @@ def main():
     n0 = unet_mod.total_kernel_launches()
     ms, outs = timed(args.steps, devt, False)
     launches = unet_mod.total_kernel_launches() - n0
+    if world > 1:  # whole-job count
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
     clocks = sampler.stop() if sampler else None
     ms_e2e, outs_h = timed(args.steps, host, True)
     if world > 1:  # gather final latents (128 KiB per image) on every rank
@@ -337,10 +365,11 @@ def main():
                                    "cores": threads, "kind": "port",
                                    "sample": f"one fp32 oracle UNet sample-forward at 128x128 latents took {t:.2f} s on "
                                              f"{threads} host threads; an image needs 296 of them (extrapolated)"}
-        print(json.dumps(out), flush=True)
+        result = json.dumps(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return result
 
 
 if __name__ == "__main__":

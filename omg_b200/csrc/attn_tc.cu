@@ -22,6 +22,7 @@
 // N = 4096; ncu: issue 58 %, MUFU 42 %, tensor 28 %).
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/omg_b200.h"
@@ -30,15 +31,25 @@
 
 namespace omg {
 
-constexpr int ATT_THREADS = 384;  // warpgroup 0: TMA + MMA warps (+2 idle), warpgroups 1,2: softmax groups
-constexpr int ATT_BQ = 128;       // rows per softmax group
+constexpr int ATT_BQ = 128;       // rows per softmax group (= one Q tile)
 constexpr int ATT_BKV = 64;       // keys per block
 constexpr int ATT_D = 64;
-constexpr int ATT_KV_STAGES = 6;
 constexpr int ATT_Q_BYTES = ATT_BQ * ATT_D * 2;    // 16 KB
 constexpr int ATT_K_BYTES = ATT_BKV * ATT_D * 2;   // 8 KB (K) ; V same
 constexpr int ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;  // 16 KB per (group, buffer)
-constexpr int ATT_SMEM = 1024 + 2 * ATT_Q_BYTES + ATT_KV_STAGES * 2 * ATT_K_BYTES + 4 * ATT_P_BYTES + 512;
+
+// G = Q tiles per CTA.  G = 2 (one CTA per SM): the two tiles share every K/V load - the choice for long key
+// sequences.  G = 1 (~98 KB smem, 256 TMEM columns, two CTAs per SM): the co-resident CTA hides the prologue /
+// epilogue latencies that dominate when there are only one or two KV blocks (cross-attention: 77 / 16 keys).
+template <int G>
+struct AttCfg {
+    static constexpr int THREADS = 128 + 128 * G;  // warpgroup 0: TMA + MMA issuer warps, then one softmax warpgroup per tile
+    static constexpr int KV_STAGES = G == 2 ? 6 : 3;
+    static constexpr int SMEM = 1024 + G * ATT_Q_BYTES + KV_STAGES * 2 * ATT_K_BYTES + G * 2 * ATT_P_BYTES + 512;
+    static constexpr int TMEM_COLS = G == 2 ? 512 : 256;
+    static constexpr int O_COL0 = G * 2 * 64;      // S_g[b] at (g*2+b)*64, O_g at O_COL0 + g*64
+    static constexpr int SOFTMAX_REGS = G == 2 ? 224 : 200;
+};
 
 struct alignas(64) AttnParams {
     CUtensorMap q_map, k_map, v_map;  // 3D (cols, tokens, batch), box (64, 128 | 64, 1), SWIZZLE_128B
@@ -59,13 +70,15 @@ struct alignas(64) AttnParams {
 //   softmax:  read S_g[b], (rare) rescale O_g, P = exp2(S*scale - m), write P_g[b] to smem  ->  p_full[g][b]
 //   MMA:      S_g[b] = Q_g K_{j+2}^T ; O_g += P_g[b] V_j  ->  p_empty[g][b]
 // S and P are double-buffered, so the softmax warps never wait for the tensor core in steady state and vice versa.
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
+template <int G>
+__global__ void __launch_bounds__(AttCfg<G>::THREADS, G == 1 ? 2 : 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
+    constexpr int ATT_KV_STAGES = AttCfg<G>::KV_STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* q_smem = smem;                                          // 2 x 16 KB
-    uint8_t* kv_smem = q_smem + 2 * ATT_Q_BYTES;                     // stages x (K 8 KB | V 8 KB)
+    uint8_t* q_smem = smem;                                          // G x 16 KB
+    uint8_t* kv_smem = q_smem + G * ATT_Q_BYTES;                     // stages x (K 8 KB | V 8 KB)
     uint8_t* p_smem = kv_smem + ATT_KV_STAGES * 2 * ATT_K_BYTES;     // [g][b] x 16 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + 4 * ATT_P_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + G * 2 * ATT_P_BYTES);
     uint64_t* q_full = bars;                        // 1
     uint64_t* kv_full = bars + 1;                   // STAGES
     uint64_t* kv_empty = kv_full + ATT_KV_STAGES;   // STAGES
@@ -76,7 +89,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int slab = blockIdx.x;  // 256-query slab
+    const int slab = blockIdx.x;  // slab of G * 128 queries
     const int head = blockIdx.y;
     const int item = blockIdx.z;
     const int nkv = (p.n_kv + ATT_BKV - 1) / ATT_BKV;
@@ -88,32 +101,33 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
         mbar_init(q_full, 1);
         for (int i = 0; i < ATT_KV_STAGES; ++i) {
             mbar_init(&kv_full[i], 1);
-            mbar_init(&kv_empty[i], 2);  // one commit per tile's MMA issuer
+            mbar_init(&kv_empty[i], G);  // one commit per tile's MMA issuer
         }
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2 * G; ++i) {
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], 4);
             mbar_init(&p_empty[i], 1);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) tmem_alloc(tmem_slot, AttCfg<G>::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     griddep_launch_dependents();
     griddep_wait();
-    // TMEM columns: S_g[b] at (g*2 + b)*64, O_g at 256 + g*64
+    // TMEM columns: S_g[b] at (g*2 + b)*64, O_g at O_COL0 + g*64
     if (warp < 4) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
       if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, 2 * ATT_Q_BYTES);
+            mbar_arrive_expect_tx(q_full, G * ATT_Q_BYTES);
             const int qb = p.q_b[item];
-            tma_load_3d(q_smem, &p.q_map, q_full, p.q_col0 + head * ATT_D, slab * 256, qb);
-            tma_load_3d(q_smem + ATT_Q_BYTES, &p.q_map, q_full, p.q_col0 + head * ATT_D, slab * 256 + 128, qb);
+            for (int g = 0; g < G; ++g)
+                tma_load_3d(q_smem + g * ATT_Q_BYTES, &p.q_map, q_full, p.q_col0 + head * ATT_D,
+                            slab * (G * ATT_BQ) + g * ATT_BQ, qb);
             int stage = 0;
             uint32_t phase = 0;
             const int kb = p.k_b[item], vb = p.v_b[item];
@@ -129,7 +143,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
                 }
             }
         }
-      } else if (warp == 1 || warp == 2) {
+      } else if (warp >= 1 && warp <= G) {
         // ------------------------------------------------------------------ MMA issuers: warp 1 -> tile 0, warp 2 -> tile 1
         // (a single issuing thread would serialise both tiles' barrier round-trips; the tensor work per event is
         // only 256 cycles)
@@ -141,7 +155,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
             const uint64_t k_desc0 = umma_desc_sw128(smem_u32(kv_smem), 1024, 16);
             const uint64_t v_desc0 = umma_desc_sw128(smem_u32(kv_smem + ATT_K_BYTES), 1024, 1024);
             const uint64_t p_desc0 = umma_desc_sw128(smem_u32(p_smem + g * 2 * ATT_P_BYTES), 1024, 16);
-            const uint32_t o_tmem_g = tmem_base + 256 + g * 64;
+            const uint32_t o_tmem_g = tmem_base + AttCfg<G>::O_COL0 + g * 64;
             auto issue_s = [&](int jb) {  // scores of block jb into S_g[jb & 1]
                 const uint64_t kd = k_desc0 + (uint64_t)((jb % ATT_KV_STAGES) * ((2 * ATT_K_BYTES) >> 4));
 #pragma unroll
@@ -180,13 +194,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
       }
     } else {
         // ------------------------------------------------------------------ softmax groups
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        if constexpr (G == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         const int g = (warp - 4) >> 2;
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t s_tmem = tmem_base + g * 128 + lane_base;
-        const uint32_t o_tmem = tmem_base + 256 + g * 64 + lane_base;
+        const uint32_t o_tmem = tmem_base + AttCfg<G>::O_COL0 + g * 64 + lane_base;
         // this row's 16 B chunk slots inside a 128 B swizzled row: slot(t) = (t ^ (row & 7)) * 16
         const uint32_t my_p = smem_u32(p_smem + g * 2 * ATT_P_BYTES) + row * 128;
         const uint32_t sw = (uint32_t)(row & 7) << 4;
@@ -283,7 +298,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
         }
 
         // finalise: out = (accumulate ? out : 0) + w * O / l
-        const int qrow = slab * 256 + g * 128 + row;
+        const int qrow = slab * (G * ATT_BQ) + g * ATT_BQ + row;
         if (qrow < p.n_q) {
             const float inv = p.out_weight / l;
             __half* op = p.out + (long long)p.out_b[item] * p.out_bs + (long long)qrow * p.out_ld + p.out_col0 +
@@ -312,7 +327,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 1) tmem_dealloc(tmem_base, AttCfg<G>::TMEM_COLS);
 }
 
 static int make_attn_map(CUtensorMap* m, const void* ptr, int cols, int ld, int tokens, long long bs, int nb,
@@ -338,8 +353,12 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
     OMG_CHECK(d->out_ld % 8 == 0 && d->out_col0 % 8 == 0 && d->out_bs % 8 == 0,
               "omg_attention: output must be 16 B aligned per row");
     static bool configured = false;
+    static int force_g = 0;
     if (!configured) {
-        OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
+        OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
+        const char* e = getenv("OMG_ATTN_TILES");  // 1 | 2: force the tiles-per-CTA variant (measurements)
+        force_g = e ? atoi(e) : 0;
         configured = true;
     }
     AttnParams p;
@@ -374,7 +393,14 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
     p.scale_log2 = d->scale * 1.4426950408889634f;
     p.out_weight = d->out_weight;
     p.accumulate = d->accumulate;
-    dim3 grid((d->n_q + 255) / 256, d->heads, d->n_items);
-    OMG_CUDA(launch_pdl(attn_tc_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, stream, p));
+    // short key sequences (cross-attention) are latency-bound: single-tile CTAs, two per SM
+    const int tiles = force_g ? force_g : (d->n_kv <= 2 * ATT_BKV ? 1 : 2);
+    if (tiles == 1) {
+        dim3 grid((d->n_q + ATT_BQ - 1) / ATT_BQ, d->heads, d->n_items);
+        OMG_CUDA(launch_pdl(attn_tc_kernel<1>, grid, dim3(AttCfg<1>::THREADS), AttCfg<1>::SMEM, stream, p));
+    } else {
+        dim3 grid((d->n_q + 2 * ATT_BQ - 1) / (2 * ATT_BQ), d->heads, d->n_items);
+        OMG_CUDA(launch_pdl(attn_tc_kernel<2>, grid, dim3(AttCfg<2>::THREADS), AttCfg<2>::SMEM, stream, p));
+    }
     return check_launch("attn_tc_kernel");
 }

@@ -628,7 +628,7 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     for (int i = 0; i < p.n_segs; ++i) k_blocks += p.segs[i].k_blocks;
     bool pair_ok = true;  // both CTAs of a pair must belong to the same stream
     for (int i = 0; i + 1 < p.n_col_groups; ++i) pair_ok = pair_ok && (p.col_group_end[i] % 256 == 0);
-    const bool pair = bn == 256 && pair_ok &&
+    const bool pair = (bn == 256 || (bn == 160 && !geglu)) && pair_ok &&
                       (d->cta_pair == 2 || (d->cta_pair == 0 && use_cta_pair(p.m_tiles, p.n_tiles, k_blocks)));
     if (pair) {
         for (int i = 0; i < 2; ++i) {
@@ -638,11 +638,12 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
             const uint64_t planes = (i == 0 && d->w_group_planes > 0) ? (uint64_t)d->w_group_planes : 1;
             const uint64_t dims[2] = {(uint64_t)kt, (uint64_t)d->N * planes};
             const uint64_t strides[2] = {1, (uint64_t)kt};
-            const uint32_t box[2] = {BK, 128};
+            const uint32_t box[2] = {BK, (uint32_t)(bn / 2)};
             if (make_tmap_f16(&p.b_maps[i], wp, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
         }
         if (!d->w2) p.b_maps[1] = p.b_maps[0];
         if (geglu) return launch_gemm<256, OMG_EPI_GEGLU, 2>(p, stream);
+        if (bn == 160) return launch_gemm<160, OMG_EPI_NONE, 2>(p, stream);
         return launch_gemm<256, OMG_EPI_NONE, 2>(p, stream);
     }
     if (geglu) return launch_gemm<256, OMG_EPI_GEGLU, 1>(p, stream);

@@ -123,7 +123,8 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int splits
     }
 }
 
-// grid = (ceil(HW*C/8 / (256*2)), B): two 16 B vectors per thread (same channel offset, rows r and r + half)
+// grid = (ceil(HW*C/8 / (256*4)), B): four 16 B vectors per thread, grid-strided so that every load instruction of a
+// warp is one contiguous 512 B run; all four loads are issued before any arithmetic
 __global__ void gn_apply_kernel(GnSrc s, int HW, int cpg, int silu, const float* __restrict__ stats,
                                 const __half* __restrict__ gamma, const __half* __restrict__ beta,
                                 __half* __restrict__ y) {
@@ -133,26 +134,23 @@ __global__ void gn_apply_kernel(GnSrc s, int HW, int cpg, int silu, const float*
     const int vec_per_row = C / 8;
     const int b = blockIdx.y;
     const size_t total = (size_t)HW * vec_per_row;
-    const size_t idx0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
-    if (idx0 >= total) return;
-    // consecutive vectors of one thread: same row unless the row ends (vec_per_row is even for C % 16 == 0)
-    size_t r = idx0 / vec_per_row;
-    int c = (int)(idx0 - r * vec_per_row) * 8;
-    const int n_vec = (idx0 + 1 < total) ? 2 : 1;
-    uint4 u[2];
-    size_t rr[2];
-    int cc[2];
-    for (int v = 0; v < n_vec; ++v) {
-        rr[v] = r;
-        cc[v] = c;
-        u[v] = gn_load8(s, (size_t)b * HW + r, c);
-        c += 8;
-        if (c >= C) {
-            c = 0;
-            ++r;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t idx0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint4 u[4];
+    size_t rr[4];
+    int cc[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const size_t idx = idx0 + v * stride;
+        if (idx < total) {
+            rr[v] = idx / vec_per_row;
+            cc[v] = (int)(idx - rr[v] * vec_per_row) * 8;
+            u[v] = gn_load8(s, (size_t)b * HW + rr[v], cc[v]);
         }
     }
-    for (int v = 0; v < n_vec; ++v) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        if (idx0 + v * stride >= total) break;
         const int c0 = cc[v];
         const uint4 gw = *reinterpret_cast<const uint4*>(gamma + c0);
         const uint4 bw = *reinterpret_cast<const uint4*>(beta + c0);
@@ -295,7 +293,7 @@ extern "C" int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int
                         1.0f / ((float)HW * (float)cpg), eps, stats));
     if (check_launch("gn_finalize_kernel")) return 1;
     const size_t nvec = (size_t)HW * (C / 8);
-    OMG_CUDA(launch_pdl(gn_apply_kernel, dim3((unsigned)((nvec + 511) / 512), B), dim3(256), 0, stream, s, HW, cpg, silu,
+    OMG_CUDA(launch_pdl(gn_apply_kernel, dim3((unsigned)((nvec + 1023) / 1024), B), dim3(256), 0, stream, s, HW, cpg, silu,
                         (const float*)stats, static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
                         static_cast<__half*>(y)));
     return check_launch("gn_apply_kernel");

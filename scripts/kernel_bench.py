@@ -80,6 +80,13 @@ for (M, N, K, tag) in [(16384, 1920, 640, "qkv640"), (16384, 5120, 640, "ff1_640
     for cp in (1, 2):
         ms = timeit(lambda: ops.linear(x, w, out=out, block_n=256, cta_pair=cp))
         report(f"pair{cp}_{tag}", ms, 2.0 * M * N * K)
+for (M, N, K, tag) in [(4096, 1280, 1280, "out1280"), (4096, 1280, 5120, "ff2_1280"), (8192, 1280, 5120, "ff2_1280_b8"),
+                       (8192, 1280, 1280, "out1280_b8"), (16384, 640, 2560, "ff2_640")]:
+    x, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+    out = torch.empty(M, N, device=dev, dtype=torch.float16)
+    for cp in (1, 2):
+        ms = timeit(lambda: ops.linear(x, w, out=out, block_n=160, cta_pair=cp))
+        report(f"pair{cp}_bn160_{tag}", ms, 2.0 * M * N * K)
 
 # ---- convs
 for (B, H, C, N, tag) in [(4, 128, 320, 320, "res128"), (4, 64, 640, 640, "res64"), (4, 32, 1280, 1280, "res32"),
