@@ -313,11 +313,18 @@ def _main():
         def prof_gemm(a_views, segs, w, N, Ktot, d_view, **kws):
             pix = d_view.W * d_view.H * d_view.B
             k_total = sum(s[4] for s in segs)
+            # algorithmic bytes: every distinct operand / result once (a 3x3 conv reads its input once, not 9x)
+            seen, a_bytes = set(), 0
+            for v in a_views:
+                if v.ptr not in seen:
+                    seen.add(v.ptr)
+                    a_bytes += 2 * v.C * v.W * v.H * v.B
+            nbytes = a_bytes + 2 * w.numel() + 2 * pix * d_view.C + (2 * pix * d_view.C if kws.get("residual") is not None else 0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             orig(a_views, segs, w, N, Ktot, d_view, **kws)
             e1.record()
-            prof.append((2.0 * pix * N * k_total, e0, e1))
+            prof.append((2.0 * pix * N * k_total, e0, e1, nbytes))
 
         main_runner = next(r for k, r in pipe._runners.items() if k[0] == "main")
         ops.gemm = prof_gemm
@@ -330,6 +337,12 @@ def _main():
         g_ms = sum(p[1].elapsed_time(p[2]) for p in prof)
         achieved = g_flops / g_ms / 1e9 if g_ms > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"] if peaks else 1400.0
+        traffic = None
+        try:  # measured DRAM bytes per launch of the same forward (ncu launch list committed under profiles/)
+            from scripts.summarize_launches import summarize
+            n_l, traffic = summarize(os.path.join(ROOT, "profiles", "r01_launches_main_unet_b4.csv"), os.devnull, "")
+        except Exception:
+            traffic = None
         flops_img = SAMPLE_FORWARDS_PER_IMAGE * unet_flops(cfg, IMAGE // 8, IMAGE // 8)
         out = {
             "metric": "1024^2 images/sec @30 steps, 2 concepts", "value": value, "unit": "images/sec",
@@ -339,7 +352,11 @@ def _main():
             "e2e": {"value": e2e, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "gemm_tc_kernel",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "gemm_tc_kernel",
+                         "traffic_note": "dram__bytes_read+write per launch, mean over the 488 gemm_tc_kernel launches of one "
+                                         "main-UNet forward, ncu cold-cache pass (profiles/r01_launches_main_unet_b4.csv)",
+                         "algorithmic_bytes_per_launch": sum(p[3] for p in prof) / max(len(prof), 1),
+                         "algorithmic_flops_per_launch": g_flops / max(len(prof), 1),
                          "launches_profiled": len(prof),
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback"},
             "unet_step_ms": {"main_b4": None},

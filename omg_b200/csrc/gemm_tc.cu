@@ -628,8 +628,9 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     for (int i = 0; i < p.n_segs; ++i) k_blocks += p.segs[i].k_blocks;
     bool pair_ok = true;  // both CTAs of a pair must belong to the same stream
     for (int i = 0; i + 1 < p.n_col_groups; ++i) pair_ok = pair_ok && (p.col_group_end[i] % 256 == 0);
+    // BN = 160 pairs are available on request but never chosen: measured 0..-8 % (profiles/r01_kernel_bench.json)
     const bool pair = (bn == 256 || (bn == 160 && !geglu)) && pair_ok &&
-                      (d->cta_pair == 2 || (d->cta_pair == 0 && use_cta_pair(p.m_tiles, p.n_tiles, k_blocks)));
+                      (d->cta_pair == 2 || (d->cta_pair == 0 && bn == 256 && use_cta_pair(p.m_tiles, p.n_tiles, k_blocks)));
     if (pair) {
         for (int i = 0; i < 2; ++i) {
             const void* wp = i == 0 ? d->w : d->w2;
