@@ -85,7 +85,8 @@ typedef struct {
     int64_t col_group_end[8];
     int32_t w_group_planes; /* 0: one weight matrix for all rows; else == n_col_groups: w is [planes][N][Ktot] and row
                              * group g multiplies with plane g (per-stream weights, e.g. W + s B_g A_g merged per concept) */
-    int32_t cta_pair;   /* 0 = auto, 1 = single-CTA tiles, 2 = CTA pairs (cta_group::2, 256 x block_n tiles; block_n 256 | 160) */
+    int32_t cta_pair;   /* 0 = auto, 1 = single-CTA tiles, 2 = CTA pairs (cta_group::2, 256 x block_n tiles; block_n 256 | 160),
+                         * 3 = tall tiles (one CTA, 256 x 160: two 128-row sub-tiles share each weight tile; block_n 160) */
 } omg_gemm_desc;
 
 int omg_gemm(const omg_gemm_desc* desc, void* stream);

@@ -68,31 +68,47 @@ struct alignas(64) GemmParams {
 // CTAS = 2: a CTA pair (cluster of 2, cta_group::2) works on a 256 x BN tile; each CTA stages its own 128 A rows and
 // HALF of the B tile, so the L2 -> smem traffic per flop drops by a third (the mainloop is TMA-latency bound: ncu shows
 // lts/xbar at ~50 % with the tensor pipe at 62 % for the 128 x 256 single-CTA tile).
-template <int BN, int CTAS = 1>
+// MT = 2 ("tall tile", single CTA): two 128-row sub-tiles share every weight tile -> a third less L2 -> smem traffic
+// per flop WITHOUT a cluster, and half as many work units.  The narrow-N GEMMs at c = 1280 (out-proj, q, FF-out,
+// N = 1280, M = 4096: 256 tiles of 128 x 160 on 148 SMs, L2-latency bound) become 128 tiles of 256 x 160 = one wave.
+// Both accumulators fill the TMEM (no second stage): the epilogue is exposed, acceptable for 1-2 tiles per CTA.
+template <int BN, int CTAS = 1, int MT = 1>
 struct GemmCfg {
-    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int A_BYTES = MT * BM * BK * 2;
     static constexpr int B_BYTES = (BN / CTAS) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - STAGING_BYTES - 2 * 256 * 4 /*bias, c1*/ - 256 /*bars*/;
+    // per-column epilogue vectors (bias | c1), one plane per sub-tile
+    static constexpr int VEC_PLANE = MT == 2 ? BN : 256;
+    static constexpr int VEC_BYTES = 2 * MT * VEC_PLANE * 4;
+    // tall tiles need the last KB for a 4th stage: they rely on the (in practice guaranteed, checked at run time)
+    // 1024 B alignment of the dynamic shared memory window instead of reserving alignment slack
+    static constexpr int ALIGN_SLACK = MT == 2 ? 0 : 1024;
+    static constexpr int BUDGET = 227 * 1024 - ALIGN_SLACK - STAGING_BYTES - VEC_BYTES - 256 /*bars*/;
     static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + 2 * 256 * 4 + 256;
-    static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator stage
+    static constexpr int SMEM_BYTES = ALIGN_SLACK + STAGES * STAGE_BYTES + STAGING_BYTES + VEC_BYTES + 256;
+    static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator
     static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+    static constexpr int ACC_STAGES = MT == 2 ? 1 : 2;  // MT = 2: the two accumulators ARE the two sub-tiles
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-template <int BN, int EPI, int CTAS>
+template <int BN, int EPI, int CTAS, int MT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-    using Cfg = GemmCfg<BN, CTAS>;
+    static_assert(MT == 1 || CTAS == 1, "tall tiles are a single-CTA variant");
+    using Cfg = GemmCfg<BN, CTAS, MT>;
+    constexpr int MSUB = CTAS * MT;  // 128-row m-tiles per work unit
     constexpr int STAGES = Cfg::STAGES;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    if constexpr (Cfg::ALIGN_SLACK == 0) {
+        if (smem != smem_raw) __trap();  // dynamic smem window not 1024 B aligned: the swizzled tiles would be garbage
+    }
     uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
     float* s_bias = reinterpret_cast<float*>(staging + STAGING_BYTES);
-    float* s_c1 = s_bias + 256;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_c1 + 256);
+    float* s_c1 = s_bias + MT * Cfg::VEC_PLANE;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_c1 + MT * Cfg::VEC_PLANE);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -103,7 +119,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     // work unit = (group of CTAS consecutive m-tiles, n-tile); CTA `cta_rank` of the pair owns m-tile unit_m*CTAS+rank
     const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
-    const int total_tiles = ((p.m_tiles + CTAS - 1) / CTAS) * p.n_tiles;
+    const int total_tiles = ((p.m_tiles + MSUB - 1) / MSUB) * p.n_tiles;
     const int unit0 = blockIdx.x / CTAS, unit_step = gridDim.x / CTAS;
     const int tiles_per_img = p.tiles_w * p.tiles_h;
 
@@ -140,10 +156,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = unit0; tile < total_tiles; tile += unit_step) {
-                const int m_tile = (tile / p.n_tiles) * CTAS + (int)cta_rank, n_tile = tile % p.n_tiles;
+                const int m_tile = (tile / p.n_tiles) * MSUB + (int)cta_rank * MT, n_tile = tile % p.n_tiles;
                 const int b = m_tile / tiles_per_img;  // >= img_b for the odd m-tile of the last pair: TMA zero-fills
                 const int rem = m_tile % tiles_per_img;
                 const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
+                // second 128-row sub-tile of a tall tile (the next m-tile in (w, h, image) order)
+                const int b1 = (m_tile + 1) / tiles_per_img, rem1 = (m_tile + 1) % tiles_per_img;
+                const int h1 = (rem1 / p.tiles_w) * p.th, w1 = (rem1 % p.tiles_w) * p.tw;
                 int n0 = n_tile * BN + (int)cta_rank * (BN / CTAS);  // this CTA's slice of the B tile
                 if (p.w_group_rows > 0) {  // multi-stream launch: this tile's stream selects the weight plane
                     const long long tile_pix0 = ((long long)b * p.img_h + h0) * p.img_w + w0;
@@ -166,6 +185,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                             tma_load_4d(a_dst, &p.a_maps[sg.a_map], &full_bar[stage], sg.a_c0 + kb * BK, w0 + sg.dx,
                                         h0 + sg.dy, b);
+                            if constexpr (MT == 2)
+                                tma_load_4d(a_dst + BM * BK * 2, &p.a_maps[sg.a_map], &full_bar[stage], sg.a_c0 + kb * BK,
+                                            w1 + sg.dx, h1 + sg.dy, b1);
                             tma_load_2d(b_dst, &p.b_maps[sg.b_map], &full_bar[stage], sg.b_k0 + kb * BK, n0);
                         }
                         if (++stage == STAGES) {
@@ -187,7 +209,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             for (int tile = unit0; tile < total_tiles; tile += unit_step) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+                const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;  // (ACC_STAGES == 1 for tall tiles: acc == 0)
                 uint32_t accumulate = 0;
                 for (int s = 0; s < p.n_segs; ++s) {
                     const int kbs = p.segs[s].k_blocks;
@@ -202,6 +224,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                             // +32 B per K=16 step inside the 128 B swizzle atom (start-address field is >>4)
                             if constexpr (CTAS == 2) tc_mma_f16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate);
                             else tc_mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate);
+                            if constexpr (MT == 2)  // second sub-tile: A rows 128..255 (+16 KB), accumulator + ACC_STRIDE
+                                tc_mma_f16_ss(d_tmem + Cfg::ACC_STRIDE, a_desc + ((BM * BK * 2) >> 4) + 2 * k, b_desc + 2 * k,
+                                              idesc, accumulate);
                             accumulate = 1;
                         }
                         if constexpr (CTAS == 2) tc_commit_pair(&empty_bar[stage]);
@@ -214,7 +239,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 }
                 if constexpr (CTAS == 2) tc_commit_pair(&tfull_bar[acc]);
                 else tc_commit(&tfull_bar[acc]);
-                if (++acc == 2) {
+                if (++acc == Cfg::ACC_STAGES) {
                     acc = 0;
                     acc_phase ^= 1;
                 }
@@ -228,15 +253,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const int ew = warp - 2;
         const int q = warp & 3;
         const int half = ew >> 2;
-        const int et = q * 32 + lane;  // row of the tile owned by this thread
+        const int et = q * 32 + lane;  // row of the (sub-)tile owned by this thread
+        // MT == 1: the two warps of a lane quarter split the column chunks by parity.  MT == 2: warp `half` owns
+        // sub-tile `half` (its own accumulator) and walks all of its chunks.
+        constexpr int CH_STEP = MT == 2 ? 1 : 2;
+        const int ch0 = MT == 2 ? 0 : half;
+        const int sub = MT == 2 ? half : 0;
         uint8_t* sbuf = staging + (q * 2 + half) * 2048;
         int acc = 0;
         uint32_t acc_phase = 0;
         constexpr int ACC_PER_CHUNK = (EPI == OMG_EPI_GEGLU) ? 64 : 32;
         constexpr int NCH = BN / ACC_PER_CHUNK;
-        constexpr int NIT = (NCH + 1) / 2;  // chunks per warp
+        constexpr int NIT = (NCH + CH_STEP - 1) / CH_STEP;  // chunks per warp
         for (int tile = unit0; tile < total_tiles; tile += unit_step) {
-            const int m_tile = (tile / p.n_tiles) * CTAS + (int)cta_rank, n_tile = tile % p.n_tiles;
+            const int m_tile = (tile / p.n_tiles) * MSUB + (int)cta_rank * MT + sub, n_tile = tile % p.n_tiles;
             const int b = m_tile / tiles_per_img;
             const int rem = m_tile % tiles_per_img;
             const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
@@ -252,7 +282,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     if (tile_pix0 >= p.col_group_end[g2]) cg = g2 + 1;
                 cg *= (size_t)p.N;
             }
-            for (int j = ew * 32 + lane; j < BN; j += 256) {
+            // per-column vectors of THIS warp group's sub-tile (tall tiles: each half fills its own 256-entry plane,
+            // the two sub-tiles may belong to different images / streams)
+            float* sbias = s_bias + sub * Cfg::VEC_PLANE;
+            float* sc1 = s_c1 + sub * Cfg::VEC_PLANE;
+            for (int j = (MT == 2 ? q * 32 + lane : ew * 32 + lane); j < BN; j += (MT == 2 ? 128 : 256)) {
                 float v = 0.f, c1 = 0.f;
                 const int n = n0 + j;
                 if (n < p.N) {
@@ -264,8 +298,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                         if (p.rowvec && b < p.img_b) v += __half2float(p.rowvec[(size_t)b * p.rowvec_ld + n]);
                     }
                 }
-                s_bias[j] = v;
-                s_c1[j] = c1;
+                sbias[j] = v;
+                sc1[j] = c1;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
 
@@ -303,17 +337,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 }
             };
             if constexpr (EPI != OMG_EPI_GEGLU) {
-                load_res(half, res[0]);
-                load_res(half + 2, res[1]);
+                load_res(ch0, res[0]);
+                load_res(ch0 + CH_STEP, res[1]);
             }
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + acc * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+            const uint32_t t_row = tmem_base + (acc + sub) * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
 
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
-                const int c = 2 * it + half;
+                const int c = CH_STEP * it + ch0;
                 if (c >= NCH) break;
                 const int nacc0 = n0 + c * ACC_PER_CHUNK;
                 if (nacc0 >= p.N) break;
@@ -323,8 +357,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     tmem_ld_32x32(t_row + c * 64, r0);
                     tmem_ld_32x32(t_row + c * 64 + 32, r1);
                     tc_wait_ld();
-                    const float* sb = s_bias + c * 64;
-                    const float* sc = s_c1 + c * 64;
+                    const float* sb = sbias + c * 64;
+                    const float* sc = sc1 + c * 64;
                     auto pair_out = [&](const uint32_t(&r)[32], int off, int i) {
                         float a, g;
                         if (ln) {
@@ -346,10 +380,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     uint32_t r[32];
                     tmem_ld_32x32(t_row + c * 32, r);
                     tc_wait_ld();
-                    const float* sb = s_bias + c * 32;
+                    const float* sb = sbias + c * 32;
                     float v[32];
                     if (ln) {
-                        const float* sc = s_c1 + c * 32;
+                        const float* sc = sc1 + c * 32;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaf(ln_a, __uint_as_float(r[j]), fmaf(ln_k, sc[j], sb[j]));
                     } else {
@@ -372,7 +406,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                                 v[j4 * 8 + 2 * t + 1] += f.y;
                             }
                         }
-                        load_res(c + 4, res[it & 1]);
+                        load_res(c + 2 * CH_STEP, res[it & 1]);
                     }
                     if (p.stats_out != nullptr) {
                         if (nacc0 + 32 <= p.N) {
@@ -412,16 +446,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     tma_store_commit();
                 }
             }
-            if (p.stats_out != nullptr && row_valid)  // one partial per (n-tile, chunk parity)
-                reinterpret_cast<float2*>(p.stats_out)[(size_t)(n_tile * 2 + half) * p.stats_rows + pix] =
-                    make_float2(row_sum, row_sq);
+            if (p.stats_out != nullptr && row_valid) {  // two partial planes per n-tile
+                float2* so = reinterpret_cast<float2*>(p.stats_out);
+                if constexpr (MT == 2) {  // this thread covered the whole row of its sub-tile
+                    so[(size_t)(n_tile * 2) * p.stats_rows + pix] = make_float2(row_sum, row_sq);
+                    so[(size_t)(n_tile * 2 + 1) * p.stats_rows + pix] = make_float2(0.f, 0.f);
+                } else {
+                    so[(size_t)(n_tile * 2 + half) * p.stats_rows + pix] = make_float2(row_sum, row_sq);
+                }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
                 if (leader) mbar_arrive(&tempty_bar[acc]);
                 else mbar_arrive_remote(&tempty_bar[acc], 0);  // the pair's MMA issuer lives in the leader CTA
             }
-            if (++acc == 2) {
+            if (++acc == Cfg::ACC_STAGES) {
                 acc = 0;
                 acc_phase ^= 1;
             }
@@ -448,23 +488,31 @@ static int view_to_tmap(CUtensorMap* m, const omg_view4& v, uint32_t box_c, uint
     return make_tmap_f16(m, v.ptr, 4, dims, strides, box, sw);
 }
 
-template <int BN, int EPI, int CTAS>
+template <int BN, int EPI, int CTAS, int MT = 1>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, CTAS>;
+    using Cfg = GemmCfg<BN, CTAS, MT>;
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
-        OMG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        OMG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, CTAS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::SMEM_BYTES));
         int dev = 0;
         OMG_CUDA(cudaGetDevice(&dev));
         OMG_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         configured = true;
     }
-    const int units = ((p.m_tiles + CTAS - 1) / CTAS) * p.n_tiles;
+    const int units = ((p.m_tiles + CTAS * MT - 1) / (CTAS * MT)) * p.n_tiles;
     const int grid = CTAS * std::min(units, num_sms / CTAS);
-    OMG_CUDA(launch_cluster(gemm_tc_kernel<BN, EPI, CTAS>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, CTAS, p));
+    OMG_CUDA(launch_cluster(gemm_tc_kernel<BN, EPI, CTAS, MT>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, CTAS, p));
     return check_launch("gemm_tc_kernel");
+}
+
+static bool use_tall_tiles(long m_tiles, long n_tiles, long k_blocks) {
+    if (m_tiles < 2 || k_blocks < 16) return false;
+    const long t1 = m_tiles * n_tiles, t2 = ((m_tiles + 1) / 2) * n_tiles;
+    const double e1 = (double)t1 / (double)(((t1 + 147) / 148) * 148);
+    const double e2 = (double)t2 / (double)(((t2 + 147) / 148) * 148);
+    return e2 * 1.10 >= e1;
 }
 
 // CTA pairs pay off when the pair-tiles still fill the 74 SM pairs about as well as single tiles fill 148 SMs
@@ -647,6 +695,10 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
         if (bn == 160) return launch_gemm<160, OMG_EPI_NONE, 2>(p, stream);
         return launch_gemm<256, OMG_EPI_NONE, 2>(p, stream);
     }
+    // tall tiles (256 x 160 per CTA): the narrow-N, long-enough-K GEMMs whose 128 x 160 tiles are L2-latency bound
+    const bool tall = bn == 160 && !geglu && pair_ok &&
+                      (d->cta_pair == 3 || (d->cta_pair == 0 && use_tall_tiles(p.m_tiles, p.n_tiles, k_blocks)));
+    if (tall) return launch_gemm<160, OMG_EPI_NONE, 1, 2>(p, stream);
     if (geglu) return launch_gemm<256, OMG_EPI_GEGLU, 1>(p, stream);
     switch (bn) {
         case 64: return launch_gemm<64, OMG_EPI_NONE, 1>(p, stream);

@@ -84,9 +84,9 @@ for (M, N, K, tag) in [(4096, 1280, 1280, "out1280"), (4096, 1280, 5120, "ff2_12
                        (8192, 1280, 1280, "out1280_b8"), (16384, 640, 2560, "ff2_640")]:
     x, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
     out = torch.empty(M, N, device=dev, dtype=torch.float16)
-    for cp in (1, 2):
+    for cp in (1, 3):
         ms = timeit(lambda: ops.linear(x, w, out=out, block_n=160, cta_pair=cp))
-        report(f"pair{cp}_bn160_{tag}", ms, 2.0 * M * N * K)
+        report(f"{'tall' if cp == 3 else 'single'}_bn160_{tag}", ms, 2.0 * M * N * K)
 
 # ---- convs
 for (B, H, C, N, tag) in [(4, 128, 320, 320, "res128"), (4, 64, 640, 640, "res64"), (4, 32, 1280, 1280, "res32"),
@@ -98,11 +98,15 @@ for (B, H, C, N, tag) in [(4, 128, 320, 320, "res128"), (4, 64, 640, 640, "res64
     xc = x.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
     wc = w.contiguous(memory_format=torch.channels_last)
     ref = timeit(lambda: F.conv2d(xc, wc, padding=1))
-    for bn in [0, 128, 160, 256]:
+    for bn in [0, 160, 256]:
         if bn == 160 and N % 160:
             continue
         ms = timeit(lambda: ops.conv3x3(x, wp, out=out, block_n=bn))
         report(f"conv3x3_{tag}_bn{bn}", ms, 2.0 * B * H * H * N * 9 * C, ref_ms=ref)
+    if N % 160 == 0:
+        for cp in (1, 3):
+            ms = timeit(lambda: ops.conv3x3(x, wp, out=out, block_n=160, cta_pair=cp))
+            report(f"conv3x3_{tag}_{'tall' if cp == 3 else 'single'}160", ms, 2.0 * B * H * H * N * 9 * C, ref_ms=ref)
 
 # ---- attention
 for (B, N, heads, tag) in [(4, 4096, 10, "self4096"), (4, 1024, 20, "self1024"), (8, 1024, 20, "self1024_b8")]:

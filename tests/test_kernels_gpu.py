@@ -311,3 +311,37 @@ def test_cta_pair_geglu_lora_conv(ops):
     out = ops.conv3x3(xi, ops.pack_conv3x3_weight(wc), bias=bc, rowvec=temb, block_n=256, cta_pair=2)
     ref = F.conv2d(xi.float().permute(0, 3, 1, 2), wc.float(), bc.float(), padding=1) + temb.float()[:, :, None, None]
     assert rel(out.permute(0, 3, 1, 2), ref) < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 1280, 1280), (2176, 640, 512), (384, 320, 128), (8192, 1280, 5120)])
+def test_linear_tall_tiles(ops, M, N, K):
+    """256 x 160 tiles in one CTA (two 128-row sub-tiles share each weight tile); odd m-tile counts included."""
+    x, w, b = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2), rnd(N, seed=3)
+    r = rnd(M, N, seed=4)
+    out = ops.linear(x, w, bias=b, residual=r, block_n=160, cta_pair=3)
+    ref = x.float() @ w.float().t() + b.float() + r.float()
+    assert rel(out, ref) < 2e-3
+    assert torch.equal(out, ops.linear(x, w, bias=b, residual=r, block_n=160, cta_pair=1))
+
+
+def test_tall_tiles_conv_rowvec_and_stats(ops):
+    from omg_b200 import _lib as L
+    B, H, W, Cin, Nc = 3, 16, 16, 128, 320          # 256 pixels per image: the two sub-tiles of a tall tile differ in image
+    xi = rnd(B, H, W, Cin, seed=7)
+    wc = rnd(Nc, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=8)
+    bc, temb = rnd(Nc, seed=9), rnd(B, Nc, seed=10)
+    out = ops.conv3x3(xi, ops.pack_conv3x3_weight(wc), bias=bc, rowvec=temb, block_n=160, cta_pair=3)
+    ref = F.conv2d(xi.float().permute(0, 3, 1, 2), wc.float(), bc.float(), padding=1) + temb.float()[:, :, None, None]
+    assert rel(out.permute(0, 3, 1, 2), ref) < 2e-3
+    # row statistics emitted by a tall-tile producer feed a folded LayerNorm
+    M, C, N = 1024, 320, 640
+    o, wo = rnd(M, C, seed=1), rnd(C, C, scale=C ** -0.5, seed=2)
+    h0 = rnd(M, C, seed=4) + 0.5
+    parts = ops.gemm_plan(C, L.EPI_NONE, M)[1]
+    stats = torch.zeros(parts, M, 2, device="cuda")
+    h = h0.clone()
+    ops.linear(o, wo, residual=h, out=h, stats_out=stats, block_n=160, cta_pair=3)
+    href = o.float() @ wo.float().t() + h0.float()
+    s = stats.sum(0)
+    assert torch.allclose(s[:, 0], href.sum(1), rtol=2e-3, atol=2e-2)
+    assert torch.allclose(s[:, 1], (href * href).sum(1), rtol=3e-3, atol=2e-2)
