@@ -1,7 +1,6 @@
-"""BASELINE.json configs 1, 3, 4 on one B200 (config 2 is bench.py's workload, config 5 its --gpus sweep).
+"""BASELINE.json configs 3, 4 on one B200 (config 2 is bench.py's workload, config 5 its --gpus sweep).
 
-  config 1  plumbing/parity at FULL SDXL widths: one fusion step (stage 2, step index 16) at 64x64 latents, 1 LoRA
-            concept, fp32 CPU oracle vs CUDA: noise prediction and latents after the step.
+  (config 1, the full-width parity check against the fp32 oracle, is tests/test_config1_gpu.py)
   config 3  OMG + InstantID, 2 identities (IP-adapter concept UNet + IdentityNet), 1024^2, 30 steps: s / image.
   config 4  4 LoRA concepts + style LoRA + spatial ControlNet on the main pass, 1024^2, 30 steps: s / image.
 Prints one JSON object per config; results are copied into BASELINE.md section 5.
@@ -24,7 +23,7 @@ from omg_b200.unet import PackedUNet, RowGroup, UNetRunner  # noqa: E402
 
 dev = "cuda"
 cfg = UNetConfig.sdxl()
-which = sys.argv[1:] or ["1", "3", "4"]
+which = sys.argv[1:] or ["3", "4"]
 
 
 def rel(a, b):
@@ -44,81 +43,6 @@ def timed_image(fn, warm=1, reps=1):
 
 
 sd = synthetic.make_state_dict(cfg, seed=0, device=dev, dtype=torch.float16)
-
-if "1" in which:
-    from oracle import p2p as op2p
-    from oracle import unet as ou
-    from oracle.pipeline import fuse_noise
-    from oracle.scheduler import EulerDiscrete
-    torch.set_num_threads(min(32, len(os.sched_getaffinity(0))))
-    H = W = 64
-    size = H * 8
-    lo = synthetic.make_lora(cfg, seed=1000, rank=32, device=dev)
-    unet = PackedUNet(cfg, sd, device=dev)
-    unet.add_lora_set("c0", [(lo, 1.0)], 0.8)
-    g = torch.Generator().manual_seed(0)
-    ctx4 = torch.randn(2, 77, 2048, generator=g).half().float()
-    ctx4 = torch.cat([ctx4[:1], ctx4[:1], ctx4[1:], ctx4[1:]])
-    pooled4 = torch.randn(2, 1280, generator=g).half().float()
-    pooled4 = torch.cat([pooled4[:1], pooled4[:1], pooled4[1:], pooled4[1:]])
-    cctx = torch.randn(2, 77, 2048, generator=g).half().float()
-    cpooled = torch.randn(2, 1280, generator=g).half().float()
-    tid = torch.tensor([[size, size, 0, 0, size, size]], dtype=torch.float32)
-    sched = EulerDiscrete()
-    ts = sched.set_timesteps(30)
-    i = 16
-    lat = (torch.randn(2, 4, H, W, generator=g) * float(sched.sigmas[i])).half().float()
-    mask = torch.zeros(size, size)
-    mask[:, : size // 2] = 1
-    lmi = sched.scale_model_input(torch.cat([lat] * 2), i).half().float()
-    # --- CUDA path: grouped forward (main rows + concept rows) and the fused step kernel
-    prompts = ["x y z"] * 2
-    ctrl = AttentionReplace(prompts, 50, {"default_": 1.0}, 0.4, size // 32, size // 32)
-    pipe = LoraMultiConceptPipeline(unet, use_graphs=False)
-    revise_regionally_controlnet_forward(pipe, ctrl)
-    ctrl.cur_step = i
-    groups = [RowGroup(0, 4, None, False), RowGroup(4, 6, "c0", False)]
-    r = UNetRunner(unet, 6, H, W, use_graphs=False, groups=groups)
-    pipe._update_p2p_context([], ctrl, ctx4, first=True)
-    r.set_conditioning([float(ts[i])], [(ctx4, None, False), (cctx, "c0", False)], torch.cat([pooled4, cpooled]),
-                       tid.repeat(6, 1), extra_ctx=pipe._p2p_rows)
-    x = torch.zeros(6, H, W, 8, dtype=torch.float16, device=dev)
-    x[:4, ..., :4] = lmi.permute(0, 2, 3, 1).half().to(dev)
-    x[4:, ..., :4] = torch.cat([lmi[3:4]] * 2).permute(0, 2, 3, 1).half().to(dev)
-    r.sample_in.copy_(x)
-    variant, _ = pipe._p2p_variant(r, ctrl, False)
-    variant["self_items"] = variant["self_items"][:4] + [(4, 4, 4, 4), (5, 5, 5, 5)]
-    variant["cross_items"] = [variant["cross_items"][0][:4] + [(4, 4, 6, 6), (5, 5, 7, 7)]]
-    variant["ip_items"] = []
-    noise = r.forward(0, variant)
-    lat_dev = lat.permute(0, 2, 3, 1).contiguous().to(dev)
-    m_lat = (torch.nn.functional.interpolate(mask[None, None], size=(H, W), mode="nearest")[0, 0] == 1).float().reshape(-1).to(dev)
-    ops.fuse_step(noise[0:4], [noise[4:6]], [m_lat], 7.5, float(sched.sigmas[i]), float(sched.sigmas[i + 1]), lat_dev)
-    torch.cuda.synchronize()
-    noise_gpu = noise[..., :4].permute(0, 3, 1, 2).float().cpu()
-    # --- fp32 oracle on the host cores (weights = the same fp16-rounded values)
-    t0 = time.perf_counter()
-    sd_cpu = {k: v.float().cpu() for k, v in sd.items()}
-    ocfg = ou.UNetConfig()
-    octrl = op2p.AttentionReplaceOracle(prompts, 50, {"default_": 1.0}, 0.4, size // 32, size // 32)
-    octrl.num_att_layers = 140
-    octrl.cur_step = i
-    with torch.no_grad():
-        n_main = ou.unet_forward(ou.Ctx(sd_cpu, ocfg, attn_core=ou.make_p2p_attn_core(octrl)), lmi, float(ts[i]), ctx4,
-                                 pooled4, tid.repeat(4, 1))
-        olo = {k: [(a.float().cpu(), b.float().cpu(), s * 0.8)] for k, (a, b, s) in lo.items()}
-        n_c = ou.unet_forward(ou.Ctx(sd_cpu, ocfg, lora=olo), torch.cat([lmi[3:4]] * 2), float(ts[i]), cctx, cpooled,
-                              tid.repeat(2, 1))
-    fused = fuse_noise(n_main, [n_c], [mask])
-    nu, nt = fused.chunk(2)
-    ref_lat = sched.step(nu + 7.5 * (nt - nu), i, lat)
-    out = {"config": 1, "desc": "SDXL widths, 64x64 latents, stage-2 step 16 (main B=4 under P2P + 1 LoRA concept B=2 as one "
-                                "grouped forward), fp32 CPU oracle vs CUDA",
-           "noise_rel_err_main": rel(noise_gpu[:4], n_main), "noise_rel_err_concept": rel(noise_gpu[4:], n_c),
-           "latent_rel_err_after_step": rel(lat_dev.permute(0, 3, 1, 2), ref_lat), "oracle_cpu_s": time.perf_counter() - t0,
-           "cpu_threads": torch.get_num_threads()}
-    print(json.dumps(out), flush=True)
-    del unet, r, pipe, sd_cpu
 
 if "3" in which:
     size = 1024
