@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libomg_b200.so")
+LIB_PATH = os.environ.get("OMG_B200_LIB") or os.path.join(_HERE, "lib", "libomg_b200.so")  # override: A/B builds
 
 OMG_MAX_A = 4
 OMG_MAX_SEGS = 12

@@ -29,6 +29,12 @@
 #include "host_common.h"
 #include "ptx.cuh"
 
+// which of the 16 element pairs of a 32-column chunk take the polynomial exp2 (FMA pipe) instead of the MUFU:
+// balances issue slots (5 per polynomial value) against the MUFU's 16 lanes / clk / SM; 5 of 16 pairs by default
+#ifndef OMG_ATT_POLY_MASK
+#define OMG_ATT_POLY_MASK 0x4924
+#endif
+
 namespace omg {
 
 constexpr int ATT_BQ = 128;       // rows per softmax group (= one Q tile)
@@ -45,9 +51,10 @@ template <int G>
 struct AttCfg {
     static constexpr int THREADS = 128 + 128 * G;  // warpgroup 0: TMA + MMA issuer warps, then one softmax warpgroup per tile
     static constexpr int KV_STAGES = G == 2 ? 6 : 3;
-    static constexpr int SMEM = 1024 + G * ATT_Q_BYTES + KV_STAGES * 2 * ATT_K_BYTES + G * 2 * ATT_P_BYTES + 512;
+    static constexpr int SMEM = 1024 + G * ATT_Q_BYTES + KV_STAGES * 2 * ATT_K_BYTES + 512;
     static constexpr int TMEM_COLS = G == 2 ? 512 : 256;
     static constexpr int O_COL0 = G * 2 * 64;      // S_g[b] at (g*2+b)*64, O_g at O_COL0 + g*64
+    static constexpr int P_COL0 = O_COL0 + G * 64;  // P_g[b] (fp16 pairs, 32 columns) at P_COL0 + (g*2+b)*32
     static constexpr int SOFTMAX_REGS = G == 2 ? 224 : 200;
 };
 
@@ -63,6 +70,7 @@ struct alignas(64) AttnParams {
     float scale_log2;  // softmax scale * log2(e)
     float out_weight;
     int accumulate;
+    int skew;  // cycles the second tile's softmax group starts late (de-phases the two groups' MUFU bursts)
 };
 
 // Pipeline (per 128-row tile g, KV block j, buffer b = j & 1):
@@ -77,8 +85,7 @@ __global__ void __launch_bounds__(AttCfg<G>::THREADS, G == 1 ? 2 : 1) attn_tc_ke
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* q_smem = smem;                                          // G x 16 KB
     uint8_t* kv_smem = q_smem + G * ATT_Q_BYTES;                     // stages x (K 8 KB | V 8 KB)
-    uint8_t* p_smem = kv_smem + ATT_KV_STAGES * 2 * ATT_K_BYTES;     // [g][b] x 16 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + G * 2 * ATT_P_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + ATT_KV_STAGES * 2 * ATT_K_BYTES);
     uint64_t* q_full = bars;                        // 1
     uint64_t* kv_full = bars + 1;                   // STAGES
     uint64_t* kv_empty = kv_full + ATT_KV_STAGES;   // STAGES
@@ -154,7 +161,7 @@ __global__ void __launch_bounds__(AttCfg<G>::THREADS, G == 1 ? 2 : 1) attn_tc_ke
             const uint64_t q_desc = umma_desc_sw128(smem_u32(q_smem + g * ATT_Q_BYTES), 1024, 16);
             const uint64_t k_desc0 = umma_desc_sw128(smem_u32(kv_smem), 1024, 16);
             const uint64_t v_desc0 = umma_desc_sw128(smem_u32(kv_smem + ATT_K_BYTES), 1024, 1024);
-            const uint64_t p_desc0 = umma_desc_sw128(smem_u32(p_smem + g * 2 * ATT_P_BYTES), 1024, 16);
+            const uint32_t p_tmem_g = tmem_base + AttCfg<G>::P_COL0 + g * 64;
             const uint32_t o_tmem_g = tmem_base + AttCfg<G>::O_COL0 + g * 64;
             auto issue_s = [&](int jb) {  // scores of block jb into S_g[jb & 1]
                 const uint64_t kd = k_desc0 + (uint64_t)((jb % ATT_KV_STAGES) * ((2 * ATT_K_BYTES) >> 4));
@@ -180,12 +187,12 @@ __global__ void __launch_bounds__(AttCfg<G>::THREADS, G == 1 ? 2 : 1) attn_tc_ke
                     tc_fence_after();
                     issue_s(j + 2);
                 }
-                const uint64_t pd = p_desc0 + (uint64_t)(b * (ATT_P_BYTES >> 4));
                 const uint64_t vd = v_desc0 + (uint64_t)(st * ((2 * ATT_K_BYTES) >> 4));
 #pragma unroll
                 for (int k = 0; k < ATT_BKV / 16; ++k) {
-                    // A = P: K-major 64-wide panel (+32 B per K step); B = V: 16 key rows (2 KB) per K step, N-major
-                    tc_mma_f16_ss(o_tmem_g, pd + 2 * k, vd + 128 * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                    // A = P from TMEM (16 keys = 8 packed columns per K step; P never touches shared memory);
+                    // B = V: 16 key rows (2 KB) per K step, N-major
+                    tc_mma_f16_ts(o_tmem_g, p_tmem_g + b * 32 + 8 * k, vd + 128 * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
                 }
                 tc_commit(&p_empty[g * 2 + b]);
                 tc_commit(&kv_empty[st]);
@@ -202,10 +209,12 @@ __global__ void __launch_bounds__(AttCfg<G>::THREADS, G == 1 ? 2 : 1) attn_tc_ke
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t s_tmem = tmem_base + g * 128 + lane_base;
         const uint32_t o_tmem = tmem_base + AttCfg<G>::O_COL0 + g * 64 + lane_base;
-        // this row's 16 B chunk slots inside a 128 B swizzled row: slot(t) = (t ^ (row & 7)) * 16
-        const uint32_t my_p = smem_u32(p_smem + g * 2 * ATT_P_BYTES) + row * 128;
-        const uint32_t sw = (uint32_t)(row & 7) << 4;
+        const uint32_t p_tmem = tmem_base + AttCfg<G>::P_COL0 + g * 64 + lane_base;
         float m = -INFINITY, l = 0.f;
+        if (G == 2 && g == 1 && p.skew > 0) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < p.skew) {}
+        }
         constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P may reach 2^8 before O is rescaled
 
         for (int j = 0; j < nkv; ++j) {
@@ -257,28 +266,35 @@ __global__ void __launch_bounds__(AttCfg<G>::THREADS, G == 1 ? 2 : 1) attn_tc_ke
             }
             // P_g[b] must have been consumed by P.V(j-2)
             mbar_wait(&p_empty[g * 2 + b], ((j >> 1) & 1) ^ 1);
-            float sum = 0.f;
-            const uint32_t rowp = my_p + b * ATT_P_BYTES;
+            uint64_t sum2 = pack_f32x2(0.f, 0.f);
+            const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2);
+            const uint64_t negm2 = pack_f32x2(-m, -m);
+            uint32_t pk[32];  // this row's 64 probabilities as fp16 pairs = the A operand of P.V, kept in TMEM
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float x0 = fmaf(__uint_as_float(sr[c][2 * i]), p.scale_log2, -m);
-                    const float x1 = fmaf(__uint_as_float(sr[c][2 * i + 1]), p.scale_log2, -m);
-                    const float p0 = fast_exp2(x0);
-                    const float p1 = (i & 1) ? poly_exp2(x1) : fast_exp2(x1);
-                    sum += p0 + p1;
-                    pk[i] = pack_half2(p0, p1);
+                    // packed fp32x2 arithmetic: one issue slot per two elements for the scale/shift and the row sum
+                    const uint64_t x2 = ffma2(pack_f32x2(__uint_as_float(sr[c][2 * i]), __uint_as_float(sr[c][2 * i + 1])),
+                                              scale2, negm2);
+                    float x0, x1, p0, p1;
+                    unpack_f32x2(x2, x0, x1);
+                    if ((OMG_ATT_POLY_MASK >> i) & 1) {  // this pair on the FMA pipe, the others on the MUFU
+                        poly_exp2_x2(x0, x1, p0, p1);
+                    } else {
+                        p0 = fast_exp2(x0);
+                        p1 = fast_exp2(x1);
+                    }
+                    sum2 = fadd2(sum2, pack_f32x2(p0, p1));
+                    pk[c * 16 + i] = pack_half2(p0, p1);
                 }
-                // K-major SWIZZLE_128B: 16 B chunk index within the 128 B row = c * 4 + t
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    st_shared_v4(rowp + (((c * 4 + t) << 4) ^ sw), pk[4 * t], pk[4 * t + 1], pk[4 * t + 2],
-                                 pk[4 * t + 3]);
             }
+            tmem_st_32x32(p_tmem + b * 32, pk);
+            float sum, sum_hi;
+            unpack_f32x2(sum2, sum, sum_hi);
+            sum += sum_hi;
             l += sum;
-            fence_proxy_async_smem();
+            tc_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[g * 2 + b]);
@@ -354,9 +370,12 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
               "omg_attention: output must be 16 B aligned per row");
     static bool configured = false;
     static int force_g = 0;
+    static int attn_skew = 0;
     if (!configured) {
         OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
         OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
+        const char* sk = getenv("OMG_ATTN_SKEW");
+        attn_skew = sk ? atoi(sk) : 0;
         const char* e = getenv("OMG_ATTN_TILES");  // 1 | 2: force the tiles-per-CTA variant (measurements)
         force_g = e ? atoi(e) : 0;
         configured = true;
@@ -393,6 +412,7 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
     p.scale_log2 = d->scale * 1.4426950408889634f;
     p.out_weight = d->out_weight;
     p.accumulate = d->accumulate;
+    p.skew = attn_skew;
     // short key sequences (cross-attention) are latency-bound: single-tile CTAs, two per SM
     const int tiles = force_g ? force_g : (d->n_kv <= 2 * ATT_BKV ? 1 : 2);
     if (tiles == 1) {

@@ -512,7 +512,7 @@ static bool use_tall_tiles(long m_tiles, long n_tiles, long k_blocks) {
     const long t1 = m_tiles * n_tiles, t2 = ((m_tiles + 1) / 2) * n_tiles;
     const double e1 = (double)t1 / (double)(((t1 + 147) / 148) * 148);
     const double e2 = (double)t2 / (double)(((t2 + 147) / 148) * 148);
-    return e2 * 1.10 >= e1;
+    return e2 * 1.20 >= e1;  // measured: a tall tile runs ~1.2x faster per row than two 128-row tiles
 }
 
 // CTA pairs pay off when the pair-tiles still fill the 74 SM pairs about as well as single tiles fill 148 SMs
@@ -526,21 +526,29 @@ static bool use_cta_pair(long m_tiles, long n_tiles, long k_blocks) {
     return e2 * 1.12 >= e1;
 }
 
-static int pick_block_n(int N, int epilogue, long m_tiles) {
+static int pick_block_n(int N, int epilogue, long m_tiles, long k_blocks = 0, bool* prefer_tall = nullptr) {
+    if (prefer_tall) *prefer_tall = false;
     if (epilogue == OMG_EPI_GEGLU) return 256;
     // time ~ waves * per-tile cost.  Per-tile costs are empirical (kernel_bench on B200, profiles/): narrow tiles
-    // re-read the A tile from shared memory once per BN columns, so cost per column rises as BN shrinks.
-    const int cands[4] = {256, 160, 128, 64};
-    const double cost[4] = {256.0, 200.0, 175.0, 110.0};
+    // re-read the A tile from shared memory once per BN columns, so cost per column rises as BN shrinks; a tall
+    // (256 x 160) tile costs ~1.2x less than two 128 x 160 tiles.  k_blocks = 0 gives the K-independent plan that
+    // omg_gemm_plan reports (row-statistics producers must all emit the same number of partials).
+    const int cands[5] = {256, 160, 128, 64, 160};
+    const double cost[5] = {256.0, 200.0, 175.0, 110.0, 333.0};
     int best = 256;
     double best_t = 1e30;
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 5; ++i) {
+        const bool tall = i == 4;
+        if (tall && (k_blocks < 16 || m_tiles < 2 || !prefer_tall)) continue;
         const long nt = (N + cands[i] - 1) / cands[i];
-        const long waves = (nt * m_tiles + 147) / 148;
-        const double t = (double)waves * cost[i];
+        const long mt = tall ? (m_tiles + 1) / 2 : m_tiles;
+        const long waves = (nt * mt + 147) / 148;
+        double t = (double)waves * cost[i];
+        if (i == 0 && k_blocks >= 16 && m_tiles >= 2) t /= 1.07;  // CTA pairs (measured +5..9 %)
         if (t < best_t - 1e-9) {
             best_t = t;
             best = cands[i];
+            if (prefer_tall) *prefer_tall = tall;
         }
     }
     return best;
@@ -599,7 +607,9 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     p.m_tiles = p.tiles_w * p.tiles_h * B;
     p.N = d->N;
     p.N_out = N_out;
-    int bn = d->block_n ? d->block_n : pick_block_n(d->N, d->epilogue, p.m_tiles);
+    bool prefer_tall = false;
+    const long k_blocks_hint = d->row_stats_out ? 0 : (long)(d->Ktot + (d->w2 ? d->K2tot : 0)) / 64;
+    int bn = d->block_n ? d->block_n : pick_block_n(d->N, d->epilogue, p.m_tiles, k_blocks_hint, &prefer_tall);
     OMG_CHECK(bn == 64 || bn == 128 || bn == 160 || bn == 256, "omg_gemm: block_n=%d unsupported", bn);
     if (geglu) bn = 256;
     p.n_tiles = (d->N + bn - 1) / bn;
@@ -697,7 +707,8 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     }
     // tall tiles (256 x 160 per CTA): the narrow-N, long-enough-K GEMMs whose 128 x 160 tiles are L2-latency bound
     const bool tall = bn == 160 && !geglu && pair_ok &&
-                      (d->cta_pair == 3 || (d->cta_pair == 0 && use_tall_tiles(p.m_tiles, p.n_tiles, k_blocks)));
+                      (d->cta_pair == 3 ||
+                       (d->cta_pair == 0 && (prefer_tall || use_tall_tiles(p.m_tiles, p.n_tiles, k_blocks))));
     if (tall) return launch_gemm<160, OMG_EPI_NONE, 1, 2>(p, stream);
     if (geglu) return launch_gemm<256, OMG_EPI_GEGLU, 1>(p, stream);
     switch (bn) {

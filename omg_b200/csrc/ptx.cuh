@@ -96,6 +96,48 @@ __device__ __forceinline__ float poly_exp2(float x) {
     return __int_as_float(__float_as_int(p) + e);
 }
 
+// ------------------------------------------------------------------ packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100)
+// one issue slot for two lanes of work: the softmax of attention at head_dim 64 is issue-slot bound
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// poly_exp2 for two values at once: 2 FMNMX + 3 FADD2 + 3 FFMA2 + 2 IMAD = 5 issue slots per value (scalar: 8)
+__device__ __forceinline__ void poly_exp2_x2(float x0, float x1, float& p0, float& p1) {
+    const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);
+    const uint64_t x = pack_f32x2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+    const uint64_t t = fadd2(x, magic);
+    const uint64_t f = fsub2(x, fsub2(t, magic));
+    uint64_t p = ffma2(f, pack_f32x2(0.055029309f, 0.055029309f), pack_f32x2(0.242256802f, 0.242256802f));
+    p = ffma2(p, f, pack_f32x2(0.693253036f, 0.693253036f));
+    p = ffma2(p, f, pack_f32x2(0.999951347f, 0.999951347f));
+    float t0, t1, q0, q1;
+    unpack_f32x2(t, t0, t1);
+    unpack_f32x2(p, q0, q1);
+    p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float d;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
