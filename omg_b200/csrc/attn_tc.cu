@@ -42,7 +42,6 @@ constexpr int ATT_BKV = 64;       // keys per block
 constexpr int ATT_D = 64;
 constexpr int ATT_Q_BYTES = ATT_BQ * ATT_D * 2;    // 16 KB
 constexpr int ATT_K_BYTES = ATT_BKV * ATT_D * 2;   // 8 KB (K) ; V same
-constexpr int ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;  // 16 KB per (group, buffer)
 
 // G = Q tiles per CTA.  G = 2 (one CTA per SM): the two tiles share every K/V load - the choice for long key
 // sequences.  G = 1 (~98 KB smem, 256 TMEM columns, two CTAs per SM): the co-resident CTA hides the prologue /

@@ -526,29 +526,32 @@ static bool use_cta_pair(long m_tiles, long n_tiles, long k_blocks) {
     return e2 * 1.12 >= e1;
 }
 
-static int pick_block_n(int N, int epilogue, long m_tiles, long k_blocks = 0, bool* prefer_tall = nullptr) {
+// k_plan: K blocks the choice is made for; k_blocks: K blocks of this launch.  Row-statistics producers of one consumer
+// must all emit the same number of partials (= 2 * n_tiles), so they - and omg_gemm_plan - choose with k_plan = "long"
+// whatever their own K; whether a 160-wide choice then runs as tall or as 128-row tiles does not change n_tiles.
+constexpr long K_PLAN_LONG = 1000;
+static int pick_block_n(int N, int epilogue, long m_tiles, long k_plan, long k_blocks, bool* prefer_tall) {
     if (prefer_tall) *prefer_tall = false;
     if (epilogue == OMG_EPI_GEGLU) return 256;
     // time ~ waves * per-tile cost.  Per-tile costs are empirical (kernel_bench on B200, profiles/): narrow tiles
     // re-read the A tile from shared memory once per BN columns, so cost per column rises as BN shrinks; a tall
-    // (256 x 160) tile costs ~1.2x less than two 128 x 160 tiles.  k_blocks = 0 gives the K-independent plan that
-    // omg_gemm_plan reports (row-statistics producers must all emit the same number of partials).
+    // (256 x 160) tile costs ~1.2x less than two 128 x 160 tiles.
     const int cands[5] = {256, 160, 128, 64, 160};
     const double cost[5] = {256.0, 200.0, 175.0, 110.0, 333.0};
     int best = 256;
     double best_t = 1e30;
     for (int i = 0; i < 5; ++i) {
         const bool tall = i == 4;
-        if (tall && (k_blocks < 16 || m_tiles < 2 || !prefer_tall)) continue;
+        if (tall && (k_plan < 16 || m_tiles < 2)) continue;
         const long nt = (N + cands[i] - 1) / cands[i];
         const long mt = tall ? (m_tiles + 1) / 2 : m_tiles;
         const long waves = (nt * mt + 147) / 148;
         double t = (double)waves * cost[i];
-        if (i == 0 && k_blocks >= 16 && m_tiles >= 2) t /= 1.07;  // CTA pairs (measured +5..9 %)
+        if (i == 0 && k_plan >= 16 && m_tiles >= 2) t /= 1.07;  // CTA pairs (measured +5..9 %)
         if (t < best_t - 1e-9) {
             best_t = t;
             best = cands[i];
-            if (prefer_tall) *prefer_tall = tall;
+            if (prefer_tall) *prefer_tall = tall && k_blocks >= 16;
         }
     }
     return best;
@@ -564,7 +567,7 @@ extern "C" int omg_gemm_plan(int N, int epilogue, int W, int H, int B, int* bloc
     while (tw / 2 >= W && tw > 1) tw /= 2;
     const int th = 128 / tw;
     const long m_tiles = (long)((W + tw - 1) / tw) * ((H + th - 1) / th) * B;
-    const int bn = pick_block_n(N, epilogue, m_tiles);
+    const int bn = pick_block_n(N, epilogue, m_tiles, K_PLAN_LONG, 0, nullptr);
     if (block_n) *block_n = bn;
     if (n_tiles) *n_tiles = 2 * ((N + bn - 1) / bn);  // row-statistics partials: one per (n-tile, chunk parity)
     return 0;
@@ -608,8 +611,10 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     p.N = d->N;
     p.N_out = N_out;
     bool prefer_tall = false;
-    const long k_blocks_hint = d->row_stats_out ? 0 : (long)(d->Ktot + (d->w2 ? d->K2tot : 0)) / 64;
-    int bn = d->block_n ? d->block_n : pick_block_n(d->N, d->epilogue, p.m_tiles, k_blocks_hint, &prefer_tall);
+    const long k_blocks_hint = (long)(d->Ktot + (d->w2 ? d->K2tot : 0)) / 64;
+    int bn = d->block_n ? d->block_n
+                        : pick_block_n(d->N, d->epilogue, p.m_tiles, d->row_stats_out ? K_PLAN_LONG : k_blocks_hint,
+                                       k_blocks_hint, &prefer_tall);
     OMG_CHECK(bn == 64 || bn == 128 || bn == 160 || bn == 256, "omg_gemm: block_n=%d unsupported", bn);
     if (geglu) bn = 256;
     p.n_tiles = (d->N + bn - 1) / bn;
