@@ -345,12 +345,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             tc_fence_after();
             const uint32_t t_row = tmem_base + (acc + sub) * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
 
-#pragma unroll
-            for (int it = 0; it < NIT; ++it) {
+            // One 32-column chunk of the accumulator.  The chunk loop below is NOT fully unrolled: fully unrolled the
+            // epilogue was ~90 KB of straight-line code executed once per tile and spent 60 % of its time in
+            // instruction-fetch stalls (ncu, profiles/r01_ncu_full_summary.csv); two bodies (one per residual
+            // prefetch buffer) stay hot in the instruction cache.
+            auto chunk = [&](const int it, uint4(&resb)[4]) {
                 const int c = CH_STEP * it + ch0;
-                if (c >= NCH) break;
+                if (c >= NCH) return;
                 const int nacc0 = n0 + c * ACC_PER_CHUNK;
-                if (nacc0 >= p.N) break;
+                if (nacc0 >= p.N) return;
                 uint32_t outp[16];
                 if constexpr (EPI == OMG_EPI_GEGLU) {
                     uint32_t r0[32], r1[32];
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     if (has_res) {
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
-                            const uint4 u = res[it & 1][j4];
+                            const uint4 u = resb[j4];
                             const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
@@ -406,7 +409,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                                 v[j4 * 8 + 2 * t + 1] += f.y;
                             }
                         }
-                        load_res(c + 2 * CH_STEP, res[it & 1]);
+                        load_res(c + 2 * CH_STEP, resb);
                     }
                     if (p.stats_out != nullptr) {
                         if (nacc0 + 32 <= p.N) {
@@ -445,6 +448,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     tma_store_4d(&p.d_map, sbuf, nout0, sw, sh, b);
                     tma_store_commit();
                 }
+            };
+#pragma unroll 1
+            for (int it = 0; it < NIT; it += 2) {
+                chunk(it, res[0]);
+                if (it + 1 < NIT) chunk(it + 1, res[1]);
             }
             if (p.stats_out != nullptr && row_valid) {  // two partial planes per n-tile
                 float2* so = reinterpret_cast<float2*>(p.stats_out);
@@ -466,7 +474,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 acc_phase ^= 1;
             }
         }
-        if (lane == 0) tma_store_wait_all<0>();
+        // the staging buffers must stay intact until the bulk stores have READ them; their global writes complete
+        // before the grid does (kernel-boundary ordering), so nothing waits for them here
+        if (lane == 0) tma_store_wait_read<0>();
     }
 
     tc_fence_before();
