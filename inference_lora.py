@@ -89,10 +89,39 @@ def build_model_synthetic(args, prompts, device):
 
 
 def build_model_sd(args, prompts, device):
-    """Real checkpoints (inference_lora.py:152-171): diffusers-layout safetensors load directly into PackedUNet.
-    Text encoders / VAE / kohya LoRA key conversion are the 'next' rows of SURVEY section 8(f)."""
-    raise SystemExit("loading real SDXL checkpoints needs the text-encoder / VAE / LoRA-format front-end that is "
-                     "scheduled after the hot path (SURVEY section 8f); run with --synthetic")
+    """Real checkpoints, mirroring the reference's build_model_sd (inference_lora.py:150-171): the diffusers-layout
+    UNet / ControlNet safetensors load straight into PackedUNet, the LoRA files (kohya / SGM / diffusers layouts) through
+    omg_b200.checkpoints, the prompts through the two CLIP towers (omg_b200.text).  Segmentation and the VAE are
+    outside the path: regions come from --mask_boxes and the outputs are latents."""
+    from omg_b200 import checkpoints as ck
+    from omg_b200.config import UNetConfig
+    from omg_b200.pipelines import ConceptModels, LoraMultiConceptPipeline, revise_regionally_controlnet_forward
+    from omg_b200.prompt_attention import AttentionReplace
+    from omg_b200.text import ClipPromptEncoder
+    from omg_b200.unet import PackedUNet
+    cfg = UNetConfig.sdxl()
+    unet = PackedUNet(cfg, ck.load_unet_weights(args.pretrained_sdxl_model, "unet"), device=device)
+    controlnet = None
+    if args.spatial_condition and os.path.isdir(args.controlnet_checkpoint):
+        controlnet = PackedUNet(cfg, ck.load_unet_weights(args.controlnet_checkpoint, "", None), device=device,
+                                controlnet=True)
+    enc = ClipPromptEncoder.from_pretrained(args.pretrained_sdxl_model, device)
+    pipe = LoraMultiConceptPipeline(unet, controlnet=controlnet, prompt_encoder=enc)
+    controller = AttentionReplace(prompts, 50, cross_replace_steps={"default_": 1.}, self_replace_steps=0.4,
+                                  tokenizer=enc.tokenizer, width=args.image_size // 32, height=args.image_size // 32)
+    revise_regionally_controlnet_forward(pipe, controller)
+    pipe_concept = ConceptModels(unet, prompt_encoder=enc)
+    if args.style_lora and os.path.exists(args.style_lora):
+        pipe.load_lora_weights(args.style_lora, weight_name="pytorch_lora_weights.safetensors", adapter_name="style")
+        pipe_concept.load_lora_weights(args.style_lora, weight_name="pytorch_lora_weights.safetensors", adapter_name="style")
+    pipe_list = []
+    for lora_path in args.lora_path.split("|"):
+        adapter_name = lora_path.split("/")[-1].split(".")[0]
+        pipe_concept.load_lora_weights(lora_path, weight_name="pytorch_lora_weights.safetensors", adapter_name=adapter_name)
+        pipe_list.append(adapter_name)
+    if not args.mask_boxes:
+        print("no --mask_boxes given: only stage 1 (the layout pass) will run")
+    return pipe, controller, pipe_concept, pipe_list, [None] * len(pipe_list)
 
 
 if __name__ == "__main__":

@@ -16,6 +16,7 @@ Per step (one iteration of lora_pipeline.py:485-632) the device executes: main U
 UNets (CUDA graphs)] -> omg_fuse_step.  No host sync happens inside the loop.
 """
 import hashlib
+import os
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -64,9 +65,11 @@ class ConceptModels:
     def _execution_device(self):
         return self.unet.device
 
-    def load_lora_weights(self, lora: dict, adapter_name: str, **_):
-        """lora: Linear path -> (A [r,in], B [out,r], alpha/r) (diffusers-format LoRA, already key-converted)."""
-        self._loras[adapter_name] = lora
+    def load_lora_weights(self, lora, adapter_name: str, weight_name: Optional[str] = None, **_):
+        """lora: a checkpoint path (file, or directory + weight_name; kohya / SGM / diffusers key layouts, see
+        omg_b200.checkpoints) as in inference_lora.py:163-169, or the converted dict Linear path -> (A [r,in],
+        B [out,r], alpha/r)."""
+        self._loras[adapter_name] = _resolve_lora(self, lora, adapter_name, weight_name)
 
     def set_adapters(self, adapter_names, adapter_weights=None):
         names = (adapter_names,) if isinstance(adapter_names, str) else tuple(adapter_names)
@@ -84,13 +87,22 @@ class ConceptModels:
         return key
 
     def encode_prompt(self, prompt, negative_prompt=None, lora_scale=None, **_):
-        pe, pp = self.prompt_encoder(prompt, lora_scale)
-        ne, np_ = self.prompt_encoder(negative_prompt or "", lora_scale)
+        kw = {}
+        if getattr(self.prompt_encoder, "supports_adapters", False):  # text-encoder LoRA of the active adapters
+            kw["adapters"] = (*self._active, getattr(self, "text_encoder_loras", {}))
+        pe, pp = self.prompt_encoder(prompt, lora_scale, **kw)
+        ne, np_ = self.prompt_encoder(negative_prompt or "", lora_scale, **kw)
         return pe[None], ne[None], pp[None], np_[None]
 
     # --- InstantID pieces (instantid_single_pieline.py:159-243) --------------------------------------------
-    def load_ip_adapter_instantid(self, image_proj_sd: dict, ip_weights: dict, heads: int = 20, dim_head: int = 64,
-                                  num_tokens: int = 16, scale: float = 0.5):
+    def load_ip_adapter_instantid(self, image_proj_sd, ip_weights: Optional[dict] = None, heads: int = 20,
+                                  dim_head: int = 64, num_tokens: int = 16, scale: float = 0.5):
+        """`load_ip_adapter_instantid(model_ckpt)` with the path of InstantID's ip-adapter.bin as in the reference
+        (instantid_single_pieline.py:159-161), or the two converted dicts."""
+        if isinstance(image_proj_sd, (str, os.PathLike)):
+            from .checkpoints import load_ip_adapter
+            image_proj_sd, ip_weights = load_ip_adapter(os.fspath(image_proj_sd), self.unet.cfg)
+            image_proj_sd = {k: v.float().to(self.unet.device) for k, v in image_proj_sd.items()}
         self.image_proj = (image_proj_sd, heads, dim_head)
         self.unet.set_ip_adapter(ip_weights, scale, num_tokens)
 
@@ -104,6 +116,22 @@ class ConceptModels:
             emb = torch.cat([torch.zeros_like(emb), emb], dim=0)
         sd, heads, dim_head = self.image_proj
         return resampler_forward(sd, emb.to(next(iter(sd.values())).device), heads, dim_head)
+
+
+def _resolve_lora(owner, lora, adapter_name: str, weight_name: Optional[str]):
+    """Path -> converted UNet LoRA dict (the text-encoder part is kept on the owner for its prompt encoder)."""
+    if not isinstance(lora, (str, os.PathLike)):
+        return lora
+    from .checkpoints import load_lora
+    path = os.fspath(lora)
+    if os.path.isdir(path):
+        path = os.path.join(path, weight_name or "pytorch_lora_weights.safetensors")
+    unet_lora, te_lora, skipped = load_lora(path, owner.unet.cfg)
+    if not hasattr(owner, "text_encoder_loras"):
+        owner.text_encoder_loras = {}
+    owner.text_encoder_loras[adapter_name] = te_lora
+    owner.skipped_lora_keys = skipped
+    return unet_lora
 
 
 def _binary_latent_mask(mask: Optional[torch.Tensor], h: int, w: int, device) -> Optional[torch.Tensor]:
@@ -144,8 +172,11 @@ class _BasePipeline:
             self._runners[key] = r
         return r
 
-    def load_lora_weights(self, lora: dict, adapter_name: str = "style", scale: float = 0.8, **_):
-        """Style LoRA on the main UNet (inference_lora.py:163; applied with cross_attention_kwargs scale 0.8)."""
+    def load_lora_weights(self, lora, adapter_name: str = "style", scale: float = 0.8,
+                          weight_name: Optional[str] = None, **_):
+        """Style LoRA on the main UNet (inference_lora.py:163; applied with cross_attention_kwargs scale 0.8); a
+        checkpoint path or a converted dict."""
+        lora = _resolve_lora(self, lora, adapter_name, weight_name)
         key = f"main:{adapter_name}@{scale:g}"
         self.unet.add_lora_set(key, [(lora, 1.0)], scale)
         self.main_lora_key = key
@@ -155,9 +186,13 @@ class _BasePipeline:
         prompts = [prompt] if isinstance(prompt, str) else list(prompt)
         negs = [negative_prompt] * len(prompts) if isinstance(negative_prompt, (str, type(None))) else list(negative_prompt)
         pe, pp, ne, np_ = [], [], [], []
+        kw = {}
+        if getattr(self.prompt_encoder, "supports_adapters", False) and getattr(self, "text_encoder_loras", None):
+            names = tuple(self.text_encoder_loras)  # the style adapter's text-encoder part (inference_lora.py:163)
+            kw["adapters"] = (names, tuple(1.0 for _ in names), self.text_encoder_loras)
         for p, n in zip(prompts, negs):
-            e, pooled = self.prompt_encoder(p, lora_scale)
-            e2, pooled2 = self.prompt_encoder(n or "", lora_scale)
+            e, pooled = self.prompt_encoder(p, lora_scale, **kw)
+            e2, pooled2 = self.prompt_encoder(n or "", lora_scale, **kw)
             pe.append(e), pp.append(pooled), ne.append(e2), np_.append(pooled2)
         return torch.stack(pe), torch.stack(ne), torch.stack(pp), torch.stack(np_)
 
