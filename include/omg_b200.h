@@ -179,6 +179,12 @@ int omg_ctx_mix(const void* ctx, const void* coef, void* out, int B, int L, int 
  * (down_block_additional_residuals / mid_block_additional_residual, src/pipelines/lora_pipeline.py:546-556). */
 int omg_axpy(const void* a, const void* b, float alpha, void* y, long long n, void* stream);
 
+/* In-place row softmax: x[r, :cols] = softmax(scale * x[r, :cols]) for an fp16 matrix with row stride ld (elements),
+ * fp32 arithmetic; cols % 8 == 0, cols <= 32768, scale > 0.  The VAE decoder's mid-block attention (one head of
+ * 512 channels: `Attention(heads=1)` inside diffusers' AutoencoderKL, reached from src/pipelines/lora_pipeline.py:649)
+ * materialises its scores with omg_gemm, normalises them here and applies them with a second omg_gemm. */
+int omg_softmax_rows(void* x, long long rows, int cols, long long ld, float scale, void* stream);
+
 /* Error string of the last failing call on this thread (never NULL). */
 const char* omg_last_error(void);
 /* Library / build identification: returns e.g. "omg_b200 sm_100a". */

@@ -66,6 +66,7 @@ SYMBOLS = {
     "omg_fuse_step": (C.c_int, [C.POINTER(FuseDesc), C.c_void_p]),
     "omg_ctx_mix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "omg_axpy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "omg_softmax_rows": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_float, C.c_void_p]),
     "omg_last_error": (C.c_char_p, []),
     "omg_version": (C.c_char_p, []),
     "omg_launch_count": (C.c_uint64, []),

@@ -150,9 +150,95 @@ __global__ void axpy_kernel(const uint4* __restrict__ a, const uint4* __restrict
     y[i] = o;
 }
 
+// In-place softmax(scale * x) over the rows of an fp16 matrix, fp32 arithmetic, one CTA per row, the row kept in
+// registers (cols <= 256 threads x MAXV vectors x 8).  Used by the VAE decoder's single-head attention (head_dim 512
+// is outside the flash kernel's d = 64), whose scores are materialised by omg_gemm.
+constexpr int SM_THREADS = 256;
+constexpr int SM_MAXV = 16;  // cols <= 32768
+__global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(__half* __restrict__ x, int cols, long long ld, float scale_log2) {
+    griddep_launch_dependents();
+    griddep_wait();
+    __shared__ float red[SM_THREADS / 32];
+    uint4* row = reinterpret_cast<uint4*>(x + (long long)blockIdx.x * ld);
+    const int nvec = cols >> 3;
+    uint4 v[SM_MAXV];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < SM_MAXV; ++i) {
+        const int j = threadIdx.x + i * SM_THREADS;
+        if (j < nvec) {
+            v[i] = row[j];
+            const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = __half22float2(h[t]);
+                mx = fmaxf(mx, fmaxf(f.x, f.y));
+            }
+        }
+    }
+    auto block_reduce = [&](float val, bool is_max) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float other = __shfl_xor_sync(0xffffffffu, val, o);
+            val = is_max ? fmaxf(val, other) : val + other;
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = val;
+        __syncthreads();
+        float r = red[0];
+#pragma unroll
+        for (int w = 1; w < SM_THREADS / 32; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+        return r;
+    };
+    // scale > 0 is checked by the host: max(scale * x) = scale * max(x)
+    const float m = block_reduce(mx, true) * scale_log2;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < SM_MAXV; ++i) {
+        const int j = threadIdx.x + i * SM_THREADS;
+        if (j < nvec) {
+            const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = __half22float2(h[t]);
+                sum += exp2f(fmaf(f.x, scale_log2, -m)) + exp2f(fmaf(f.y, scale_log2, -m));
+            }
+        }
+    }
+    const float inv = 1.0f / block_reduce(sum, false);
+    // the exponentials are recomputed rather than kept: the kernel is HBM-bound and the row already fills the registers
+#pragma unroll
+    for (int i = 0; i < SM_MAXV; ++i) {
+        const int j = threadIdx.x + i * SM_THREADS;
+        if (j < nvec) {
+            const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+            uint4 o;
+            __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = __half22float2(h[t]);
+                ho[t] = __floats2half2_rn(exp2f(fmaf(f.x, scale_log2, -m)) * inv, exp2f(fmaf(f.y, scale_log2, -m)) * inv);
+            }
+            row[j] = o;
+        }
+    }
+}
+
 }  // namespace omg
 
 using namespace omg;
+
+extern "C" int omg_softmax_rows(void* x, long long rows, int cols, long long ld, float scale, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    OMG_CHECK(x && rows >= 1 && rows <= 0x7fffffffLL, "omg_softmax_rows: bad arguments");
+    OMG_CHECK(cols >= 8 && cols % 8 == 0 && cols <= SM_THREADS * SM_MAXV * 8 && ld % 8 == 0 && ld >= cols,
+              "omg_softmax_rows: cols=%d must be a multiple of 8 and <= %d, ld a multiple of 8", cols,
+              SM_THREADS * SM_MAXV * 8);
+    OMG_CHECK(scale > 0.f, "omg_softmax_rows: scale must be positive");
+    OMG_CUDA(launch_pdl(softmax_rows_kernel, dim3((unsigned)rows), dim3(SM_THREADS), 0, stream,
+                        static_cast<__half*>(x), cols, ld, scale * 1.4426950408889634f));
+    return check_launch("softmax_rows_kernel");
+}
 
 extern "C" int omg_axpy(const void* a, const void* b, float alpha, void* y, long long n, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

@@ -247,6 +247,15 @@ def axpy(a, b, alpha=1.0, out=None):
     return out
 
 
+def softmax_rows(x, scale=1.0):
+    """In-place softmax(scale * x) over the last dimension of a 2-D fp16 matrix (rows may be strided)."""
+    _chk16(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    L.check(L.load().omg_softmax_rows(_ptr(x), x.shape[0], x.shape[1], x.stride(0), float(scale), _stream()),
+            "omg_softmax_rows")
+    return x
+
+
 def ctx_mix(ctx, coef, out=None):
     _chk16(ctx)
     B, Lk, Cc = ctx.shape

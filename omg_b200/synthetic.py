@@ -83,3 +83,21 @@ def rect_masks(n: int, size=(1024, 1024), device="cpu") -> List[torch.Tensor]:
         m[H // 8: 7 * H // 8, x0:x1] = 1.0
         out.append(m)
     return out
+
+
+def make_vae_state_dict(cfg=None, seed: int = 0, device="cpu", dtype=torch.float32):
+    """Random-init VAE decoder weights (diffusers AutoencoderKL keys) with O(1) activations through the stack."""
+    from .vae import VaeConfig, vae_decoder_param_shapes
+    cfg = cfg or VaeConfig.sdxl()
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+    for name, shape in vae_decoder_param_shapes(cfg).items():
+        if name.endswith(".bias"):
+            t = torch.randn(shape, generator=g, device=device) * 0.05
+        elif len(shape) == 1:
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g, device=device)
+        else:
+            fan_in = shape[1] * (shape[2] * shape[3] if len(shape) == 4 else 1)
+            t = torch.randn(shape, generator=g, device=device) * fan_in ** -0.5
+        sd[name] = t.to(dtype)
+    return sd
