@@ -374,6 +374,27 @@ def _main():
             e1.record()
             torch.cuda.synchronize()
             out["unet_step_ms"]["main_b4"] = e0.elapsed_time(e1) / 5
+        if world == 1:
+            # informational, outside the metric (which is defined on latents): the step after the loop
+            # (lora_pipeline.py:634-661), both images of a stage decoded to 1024^2 by omg_b200.vae
+            from omg_b200 import synthetic
+            from omg_b200.vae import PackedVaeDecoder, VaeConfig, vae_decoder_flops
+            vcfg = VaeConfig.sdxl()
+            dec = PackedVaeDecoder(synthetic.make_vae_state_dict(vcfg, 0, device=dev), vcfg, device=dev)
+            vlat = (torch.randn(2, 4, IMAGE // 8, IMAGE // 8, device=dev) * 0.4).half()
+            dec.decode(vlat)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                dec.decode(vlat)
+            e1.record()
+            torch.cuda.synchronize()
+            vms = e0.elapsed_time(e1) / 3
+            out["vae_decode"] = {"ms_per_stage": vms, "images": 2,
+                                 "tflops": 2 * vae_decoder_flops(vcfg, IMAGE // 8, IMAGE // 8) / vms / 1e9,
+                                 "note": "not inside value / e2e (metric is quoted on latents); two decodes per image"}
+            del dec, vlat
         if not args.no_cpu_baseline and world == 1:
             threads = host_threads()
             sd_cpu = cpu_state_dict(cfg, dev)

@@ -68,6 +68,7 @@ def parse_args():
     p.add_argument("--num_inference_steps", default=50, type=int)
     p.add_argument("--image_size", default=1024, type=int)
     p.add_argument("--tiny", action="store_true", help="with --synthetic: toy widths (plumbing check)")
+    p.add_argument("--decode", action="store_true", help="with --synthetic: decode with a random-init VAE decoder")
     p.add_argument("--mask_boxes", default="", type=str, help="x0,y0,x1,y1|x0,y0,x1,y1 (pixels), replaces segmentation")
     return p.parse_args()
 
@@ -106,7 +107,12 @@ def build_model_sd(args, prompts, device):
         controlnet = PackedUNet(cfg, ck.load_unet_weights(args.controlnet_checkpoint, "", None), device=device,
                                 controlnet=True)
     enc = ClipPromptEncoder.from_pretrained(args.pretrained_sdxl_model, device)
-    pipe = LoraMultiConceptPipeline(unet, controlnet=controlnet, prompt_encoder=enc)
+    vae = None
+    if os.path.isdir(os.path.join(args.pretrained_sdxl_model, "vae")):
+        from omg_b200.vae import PackedVaeDecoder
+        # fp16 activations: needs the fp16-safe re-export of the SDXL VAE weights (same keys); see omg_b200/vae.py
+        vae = PackedVaeDecoder(ck.load_unet_weights(args.pretrained_sdxl_model, "vae"), device=device)
+    pipe = LoraMultiConceptPipeline(unet, controlnet=controlnet, prompt_encoder=enc, vae_decoder=vae)
     controller = AttentionReplace(prompts, 50, cross_replace_steps={"default_": 1.}, self_replace_steps=0.4,
                                   tokenizer=enc.tokenizer, width=args.image_size // 32, height=args.image_size // 32)
     revise_regionally_controlnet_forward(pipe, controller)
@@ -134,6 +140,14 @@ if __name__ == "__main__":
     kwargs = {"height": height, "width": width, "spatial_condition": None, "output_type": "latent"}
     build = build_model_synthetic if args.synthetic else build_model_sd
     pipe, controller, pipe_concepts, pipe_list, synth_masks = build(args, prompts, device)
+    if args.synthetic and args.decode:
+        from omg_b200 import synthetic
+        from omg_b200.vae import PackedVaeDecoder, VaeConfig
+        vcfg = VaeConfig.tiny() if args.tiny else VaeConfig.sdxl()
+        pipe.vae_decoder = PackedVaeDecoder(synthetic.make_vae_state_dict(vcfg, 0), vcfg, device=device)
+    decoded = pipe.vae_decoder is not None
+    if decoded:
+        kwargs["output_type"] = "pil"  # lora_pipeline.py:634-661: VAE decode + postprocess
     styleL = bool(args.style_lora) and os.path.exists(args.style_lora)
     input_prompt = [prompts, prepare_text(args.prompt, args.prompt_rewrite)[1]]
     common = dict(input_prompt=input_prompt, concept_models=pipe_concepts,
@@ -160,7 +174,10 @@ if __name__ == "__main__":
     os.makedirs(save_dir, exist_ok=True)
     print(f"save to: {save_dir}")
     for idx, name in ((0, "stage-1"), (1, "stage-2")):
-        torch.save(image[idx].cpu(), os.path.join(save_dir, name + ".pt"))
-        _latents_png(image[idx], os.path.join(save_dir, name + ".png"))
+        if decoded:
+            image[idx].save(os.path.join(save_dir, name + ".png"))
+        else:
+            torch.save(image[idx].cpu(), os.path.join(save_dir, name + ".pt"))
+            _latents_png(image[idx], os.path.join(save_dir, name + ".png"))
     with open(os.path.join(save_dir, f"**---{args.suffix}---{hash_code}.txt"), "w") as fw:
         fw.writelines(configs)
