@@ -182,9 +182,11 @@ def embeddings(c: Ctx, timestep, text_embeds, time_ids, batch):
     cfg = c.cfg
     t = torch.as_tensor(timestep, dtype=torch.float32).reshape(-1)
     t = t.expand(batch) if t.numel() == 1 else t
-    t_emb = timestep_embedding(t, cfg.block_out_channels[0])
+    wdt = c.w("time_embedding.linear_1.weight").dtype  # diffusers: t_emb.to(dtype=sample.dtype); fp32 here unless the
+    dev = c.w("time_embedding.linear_1.weight").device  # oracle is run as the fp16 library path (tests only)
+    t_emb = timestep_embedding(t.to(dev), cfg.block_out_channels[0]).to(wdt)
     emb = linear(c, "time_embedding.linear_2", F.silu(linear(c, "time_embedding.linear_1", t_emb)))
-    tid = timestep_embedding(time_ids.reshape(-1), cfg.addition_time_embed_dim).reshape(batch, -1)
+    tid = timestep_embedding(time_ids.reshape(-1), cfg.addition_time_embed_dim).reshape(batch, -1).to(wdt)
     add = torch.cat([text_embeds, tid], dim=-1)
     aug = linear(c, "add_embedding.linear_2", F.silu(linear(c, "add_embedding.linear_1", add)))
     return emb + aug

@@ -96,6 +96,24 @@ def test_config1_full_width_fusion_step():
            "noise_rel_err_main": rel(noise_gpu[:4], n_main), "noise_rel_err_concept": rel(noise_gpu[4:], n_c),
            "latent_rel_err_after_step": rel(lat_dev.permute(0, 3, 1, 2), ref_lat), "oracle_cpu_s": time.perf_counter() - t0,
            "cpu_threads": torch.get_num_threads()}
+    # --- the reference's own arithmetic for context: the same restatement run as fp16 torch eager on the GPU
+    # (fp16 weights and activations, materialised fp16 probabilities, un-merged LoRA = the diffusers / peft library
+    # path): how far THAT is from fp32, and how far the CUDA path is from it
+    sd_h = {k: v.half().to(dev) for k, v in sd.items()}
+    hctrl = op2p.AttentionReplaceOracle(prompts, 50, {"default_": 1.0}, 0.4, size // 32, size // 32)
+    hctrl.num_att_layers, hctrl.cur_step = 140, i
+    hctrl.mapper = hctrl.mapper.to(dev)
+    hctrl.cross_replace_alpha = hctrl.cross_replace_alpha.to(dev).half()
+    hd = lambda t: t.half().to(dev)  # noqa: E731
+    with torch.no_grad():
+        h_main = ou.unet_forward(ou.Ctx(sd_h, ocfg, attn_core=ou.make_p2p_attn_core(hctrl)), hd(lmi), float(ts[i]),
+                                 hd(ctx4), hd(pooled4), tid.repeat(4, 1).to(dev))
+        hlo = {k: [(hd(a), hd(b), s * 0.8)] for k, (a, b, s) in lo.items()}
+        h_c = ou.unet_forward(ou.Ctx(sd_h, ocfg, lora=hlo), hd(torch.cat([lmi[3:4]] * 2)), float(ts[i]), hd(cctx),
+                              hd(cpooled), tid.repeat(2, 1).to(dev))
+    out["fp16_eager_rel_err_main"] = rel(h_main, n_main)
+    out["fp16_eager_rel_err_concept"] = rel(h_c, n_c)
+    out["cuda_vs_fp16_eager_main"] = rel(noise_gpu[:4], h_main)
     print(out)
     assert out["noise_rel_err_main"] < 5e-3 and out["noise_rel_err_concept"] < 5e-3
     assert out["latent_rel_err_after_step"] < 3e-3
