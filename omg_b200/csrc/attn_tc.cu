@@ -69,7 +69,6 @@ struct alignas(64) AttnParams {
     float scale_log2;  // softmax scale * log2(e)
     float out_weight;
     int accumulate;
-    int skew;  // cycles the second tile's softmax group starts late (de-phases the two groups' MUFU bursts)
 };
 
 // Pipeline (per 128-row tile g, KV block j, buffer b = j & 1):
@@ -210,10 +209,6 @@ __global__ void __launch_bounds__(AttCfg<G>::THREADS, G == 1 ? 2 : 1) attn_tc_ke
         const uint32_t o_tmem = tmem_base + AttCfg<G>::O_COL0 + g * 64 + lane_base;
         const uint32_t p_tmem = tmem_base + AttCfg<G>::P_COL0 + g * 64 + lane_base;
         float m = -INFINITY, l = 0.f;
-        if (G == 2 && g == 1 && p.skew > 0) {
-            const long long t0 = clock64();
-            while (clock64() - t0 < p.skew) {}
-        }
         constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P may reach 2^8 before O is rescaled
 
         for (int j = 0; j < nkv; ++j) {
@@ -369,12 +364,9 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
               "omg_attention: output must be 16 B aligned per row");
     static bool configured = false;
     static int force_g = 0;
-    static int attn_skew = 0;
     if (!configured) {
         OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
         OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
-        const char* sk = getenv("OMG_ATTN_SKEW");
-        attn_skew = sk ? atoi(sk) : 0;
         const char* e = getenv("OMG_ATTN_TILES");  // 1 | 2: force the tiles-per-CTA variant (measurements)
         force_g = e ? atoi(e) : 0;
         configured = true;
@@ -411,7 +403,6 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
     p.scale_log2 = d->scale * 1.4426950408889634f;
     p.out_weight = d->out_weight;
     p.accumulate = d->accumulate;
-    p.skew = attn_skew;
     // short key sequences (cross-attention) are latency-bound: single-tile CTAs, two per SM
     const int tiles = force_g ? force_g : (d->n_kv <= 2 * ATT_BKV ? 1 : 2);
     if (tiles == 1) {
