@@ -9,17 +9,19 @@
 //   * `accumulate` + `out_weight` add a second separately-normalised term    -> txt + scale * ip, and the general
 //     cross-attention edit  P_0 (M diag(a) V_1) + P_1 (diag(1-a) V_1).
 //
-// CTA = one (item, head, 256-query slab): two 128-row Q tiles ping-pong through one MMA issuer so the tensor core
-// works on one tile while the other tile's softmax runs.  384 threads = 3 warpgroups: warp 0 TMA, warp 1 tcgen05.mma
-// issuer (setmaxnreg gives their registers away), warps 4-7 / 8-11 softmax groups (one query row per thread: TMEM
-// lane == row, so no shuffles are needed; 224 registers each hold a whole 128-key score row).
-// KV blocks are 64 keys; TMEM: S_g[2] (2 x 64 cols of fp32 scores per tile, double-buffered) | O0 | O1 (64 cols each,
-// the running P.V accumulator of each tile).
+// CTA = one (item, head, 256-query slab): two 128-row Q tiles, each with its own MMA issuer warp, so the tensor core
+// works on one tile while the other tile's softmax runs.  384 threads = 3 warpgroups: warp 0 TMA, warps 1-2
+// tcgen05.mma issuers (setmaxnreg gives their registers away), warps 4-7 / 8-11 softmax groups (one query row per
+// thread: TMEM lane == row, so no shuffles are needed).
+// KV blocks are 64 keys; TMEM per tile: S_g[2] (2 x 64 columns of fp32 scores, double-buffered), O_g (64 columns, the
+// running P.V accumulator) and P_g[2] (2 x 32 columns: the probabilities as fp16 pairs).  P never touches shared
+// memory: P.V is a TS-MMA with the A operand in TMEM (the SS form moved 32 KB more shared-memory traffic per tile and
+// KV block and was shared-memory-bandwidth bound: 529 -> 597 TFLOP/s at N = 4096).
 // Softmax follows the lazy-rescale scheme: O stays in TMEM and is accumulated by the tensor core across KV blocks;
 // the running maximum is allowed to go stale by up to 2^8 and O is only rescaled (TMEM load-scale-store) when a row
-// maximum grows beyond that, which after the first blocks is rare.  exp2 runs on the MUFU for 3 of 4 elements and as
-// a degree-3 polynomial on the FMA pipe for the 4th (measured: 526 TFLOP/s with the split, 481 with MUFU only at
-// N = 4096; ncu: issue 58 %, MUFU 42 %, tensor 28 %).
+// maximum grows beyond that, which after the first blocks is rare.  The arithmetic is packed fp32x2 (FFMA2 / FADD2);
+// exp2 runs on the MUFU for 11 of 16 element pairs and as a degree-3 polynomial on the FMA pipe for the other 5
+// (MUFU only: 529 TFLOP/s; ncu in profiles/r01_ncu_full_summary.csv).
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
@@ -44,7 +46,7 @@ constexpr int ATT_Q_BYTES = ATT_BQ * ATT_D * 2;    // 16 KB
 constexpr int ATT_K_BYTES = ATT_BKV * ATT_D * 2;   // 8 KB (K) ; V same
 
 // G = Q tiles per CTA.  G = 2 (one CTA per SM): the two tiles share every K/V load - the choice for long key
-// sequences.  G = 1 (~98 KB smem, 256 TMEM columns, two CTAs per SM): the co-resident CTA hides the prologue /
+// sequences.  G = 1 (~66 KB smem, 256 TMEM columns, two CTAs per SM): the co-resident CTA hides the prologue /
 // epilogue latencies that dominate when there are only one or two KV blocks (cross-attention: 77 / 16 keys).
 template <int G>
 struct AttCfg {
@@ -73,7 +75,7 @@ struct alignas(64) AttnParams {
 
 // Pipeline (per 128-row tile g, KV block j, buffer b = j & 1):
 //   MMA:      S_g[b] = Q_g K_j^T  (issued two blocks ahead)   ->  s_full[g][b]
-//   softmax:  read S_g[b], (rare) rescale O_g, P = exp2(S*scale - m), write P_g[b] to smem  ->  p_full[g][b]
+//   softmax:  read S_g[b], (rare) rescale O_g, P = exp2(S*scale - m), P_g[b] -> TMEM (fp16 pairs)  ->  p_full[g][b]
 //   MMA:      S_g[b] = Q_g K_{j+2}^T ; O_g += P_g[b] V_j  ->  p_empty[g][b]
 // S and P are double-buffered, so the softmax warps never wait for the tensor core in steady state and vice versa.
 template <int G>
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(AttCfg<G>::THREADS, G == 1 ? 2 : 1) attn_tc_ke
             for (int j = 0; j < nkv; ++j) {
                 const int b = j & 1;
                 const int st = j % ATT_KV_STAGES;
-                mbar_wait(&p_full[g * 2 + b], (j >> 1) & 1);  // P_g[b] is in smem and S_g[b] has been read out
+                mbar_wait(&p_full[g * 2 + b], (j >> 1) & 1);  // P_g[b] is in TMEM and S_g[b] has been read out
                 tc_fence_after();
                 if (j + 2 < nkv) {  // refill the score buffer that was just released
                     wait_kv(j + 2);
