@@ -158,6 +158,10 @@ class _BasePipeline:
         self.main_lora_key: Optional[str] = None
         self._runners: Dict[tuple, UNetRunner] = {}
         self.timings: Dict[str, float] = {}
+        # opt-in exact work de-duplication (SURVEY 8d "legal algebraic dedup"), off by default = as the reference executes
+        self.dedup = False
+        self._prefix: Optional[dict] = None
+        self.sample_forwards = 0  # UNet sample-forwards executed by the last call (296 per image as-executed)
 
     @property
     def _execution_device(self):
@@ -316,8 +320,51 @@ class _BasePipeline:
         cbuf[..., :4] = torch.cat([x0[1:2], x0[1:2]], dim=0)
         lat = lat.contiguous()
         n_att = self.unet.num_attention_layers()
-        for i in range(len(ts)):
+        self.sample_forwards = 0
+        # ---- opt-in de-duplication of bitwise-identical work (results unchanged; bench reports it as "effective")
+        #  * twin rows: until the first fusion step image 1 IS image 0 (same latents, same prompt, and the
+        #    prompt-to-prompt edit of identical rows is the identity), so the main UNet runs B=2 [uncond, cond];
+        #  * stage-2 prefix: steps 0..15 of stage 2 repeat stage 1 on the same inputs, so stage 2 resumes from the
+        #    latents stage 1 had after step 15.
+        dd = self.dedup and cn is None
+        twin = dd and bool(torch.equal(lat[0], lat[1]) and torch.equal(ctx4[0], ctx4[1]) and torch.equal(ctx4[2], ctx4[3])
+                           and torch.equal(pooled4[0], pooled4[1]) and torch.equal(pooled4[2], pooled4[3]))
+        i0 = 0
+        sig_key = (tuple(float(t) for t in ts), float(guidance_scale), self.main_lora_key, h, w)
+        if dd and stage == 2 and n_act > 0 and len(ts) > FUSION_AFTER_STEP + 1 and self._prefix is not None:
+            pf = self._prefix
+            if (pf["key"] == sig_key and torch.equal(pf["lat0"], lat) and torch.equal(pf["ctx4"], ctx4.to(dev))
+                    and torch.equal(pf["pooled4"], pooled4.to(dev))):
+                i0 = FUSION_AFTER_STEP + 1
+                lat.copy_(pf["lat"])
+                main.sample_in.copy_(pf["sample_in"])
+                cbuf.copy_(pf["cbuf"])
+                if controller is not None:
+                    for _ in range(i0):
+                        controller.advance(n_att)
+        twin = twin and (n_act == 0 or i0 <= FUSION_AFTER_STEP)  # any step left that runs without fusion?
+        main2 = noise4 = None
+        if twin:
+            main2 = self._runner("main2", self.unet, 2, h, w, groups=[RowGroup(0, 2, self.main_lora_key, False)])
+            main2.set_conditioning(ts, ctx4[[0, 2]], pooled4[[0, 2]], tid.repeat(2, 1))
+            noise4 = torch.empty((4, h, w, 8), dtype=torch.float16, device=dev)
+        lat0_keep = lat.clone() if (dd and stage == 1) else None
+        for i in range(i0, len(ts)):
             fuse = i > FUSION_AFTER_STEP and n_act > 0
+            if twin and not fuse:
+                main2.sample_in.copy_(main.sample_in.view(2, 2, h, w, 8)[:, 0])
+                n2 = main2.forward(i, main2.default_variant(), key=("twin",))
+                noise4.view(2, 2, h, w, 8).copy_(n2[:, None])
+                if controller is not None:
+                    controller.advance(n_att)
+                self.sample_forwards += 2
+                ops.fuse_step(noise4, [], [], guidance_scale, float(sig[i]), float(sig[i + 1]), lat, main.sample_in, cbuf)
+                if lat0_keep is not None and i == FUSION_AFTER_STEP:
+                    self._prefix = {"key": sig_key, "lat0": lat0_keep, "ctx4": ctx4.to(dev).clone(),
+                                    "pooled4": pooled4.to(dev).clone(), "lat": lat.clone(),
+                                    "sample_in": main.sample_in.clone(), "cbuf": cbuf.clone()}
+                continue
+            twin = False  # from the first fusion step on the two images differ
             if controller is not None:
                 self._update_p2p_context(p2p_runners, controller, ctx4, first=False)
             run = fused if (fuse and grouped) else main
@@ -372,8 +419,13 @@ class _BasePipeline:
                             ckey = ("concept", "id", id_scale)
                         noises.append(r.forward(i, v, key=ckey))
                 fmasks = [masks[k] for k in active]
+            self.sample_forwards += 4 + (2 * n_act if fuse else 0)
             ops.fuse_step(noise[0:4] if run is fused else noise, noises, fmasks, guidance_scale, float(sig[i]),
                           float(sig[i + 1]), lat, main.sample_in, cbuf)
+            if lat0_keep is not None and i == FUSION_AFTER_STEP:
+                self._prefix = {"key": sig_key, "lat0": lat0_keep, "ctx4": ctx4.to(dev).clone(),
+                                "pooled4": pooled4.to(dev).clone(), "lat": lat.clone(),
+                                "sample_in": main.sample_in.clone(), "cbuf": cbuf.clone()}
         return lat
 
     def _finish(self, latents_nhwc: torch.Tensor, output_type: str, return_dict: bool):
