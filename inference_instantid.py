@@ -84,6 +84,8 @@ def parse_args():
     p.add_argument("--controlnet_conditioning_scale", default=0.8, type=float)
     p.add_argument("--ip_adapter_scale", default=0.8, type=float)
     # additions
+    p.add_argument("--dedup", action="store_true", help="skip work that repeats identical work (same outputs): twin "
+                   "rows before the first fusion step, stage-2 steps 0..15")
     p.add_argument("--synthetic", action="store_true")
     p.add_argument("--tiny", action="store_true")
     p.add_argument("--num_inference_steps", default=50, type=int)
@@ -140,6 +142,7 @@ if __name__ == "__main__":
     device = torch.device("cuda")
     from omg_b200 import synthetic
     pipe, controller, cm = build_synthetic(args, device)
+    pipe.dedup = args.dedup
     cm.set_ip_adapter_scale(args.ip_adapter_scale)
     size = args.image_size
     prompts = [args.prompt] * 2

@@ -64,6 +64,8 @@ def parse_args():
     p.add_argument("--seed", default=14, type=int)
     p.add_argument("--suffix", default="", type=str)
     # additions
+    p.add_argument("--dedup", action="store_true", help="skip work that repeats identical work (same outputs): twin "
+                   "rows before the first fusion step, stage-2 steps 0..15")
     p.add_argument("--synthetic", action="store_true", help="random-init SDXL-shaped weights, synthetic encoders/masks")
     p.add_argument("--num_inference_steps", default=50, type=int)
     p.add_argument("--image_size", default=1024, type=int)
@@ -140,6 +142,7 @@ if __name__ == "__main__":
     kwargs = {"height": height, "width": width, "spatial_condition": None, "output_type": "latent"}
     build = build_model_synthetic if args.synthetic else build_model_sd
     pipe, controller, pipe_concepts, pipe_list, synth_masks = build(args, prompts, device)
+    pipe.dedup = args.dedup
     if args.synthetic and args.decode:
         from omg_b200 import synthetic
         from omg_b200.vae import PackedVaeDecoder, VaeConfig
