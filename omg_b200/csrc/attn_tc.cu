@@ -9,10 +9,10 @@
 //   * `accumulate` + `out_weight` add a second separately-normalised term    -> txt + scale * ip, and the general
 //     cross-attention edit  P_0 (M diag(a) V_1) + P_1 (diag(1-a) V_1).
 //
-// CTA = one (item, head, 256-query slab): two 128-row Q tiles, each with its own MMA issuer warp, so the tensor core
-// works on one tile while the other tile's softmax runs.  384 threads = 3 warpgroups: warp 0 TMA, warps 1-2
-// tcgen05.mma issuers (setmaxnreg gives their registers away), warps 4-7 / 8-11 softmax groups (one query row per
-// thread: TMEM lane == row, so no shuffles are needed).
+// CTA = one (item, head, 128-query tile), two CTAs per SM (template G = 1; G = 2 puts two tiles into one CTA): 256
+// threads = warp 0 TMA, warp 1 tcgen05.mma issuer (setmaxnreg gives their registers away), warps 4-7 softmax (one
+// query row per thread: TMEM lane == row, so no shuffles are needed).  While one CTA's softmax runs the tensor core
+// works for the co-resident CTA, and within a CTA S is double-buffered (S(j+2) and P.V(j) run during softmax(j+1)).
 // KV blocks are 64 keys; TMEM per tile: S_g[2] (2 x 64 columns of fp32 scores, double-buffered), O_g (64 columns, the
 // running P.V accumulator) and P_g[2] (2 x 32 columns: the probabilities as fp16 pairs).  P never touches shared
 // memory: P.V is a TS-MMA with the A operand in TMEM (the SS form moved 32 KB more shared-memory traffic per tile and
@@ -45,13 +45,13 @@ constexpr int ATT_D = 64;
 constexpr int ATT_Q_BYTES = ATT_BQ * ATT_D * 2;    // 16 KB
 constexpr int ATT_K_BYTES = ATT_BKV * ATT_D * 2;   // 8 KB (K) ; V same
 
-// G = Q tiles per CTA.  G = 2 (one CTA per SM): the two tiles share every K/V load - the choice for long key
-// sequences.  G = 1 (~66 KB smem, 256 TMEM columns, two CTAs per SM): the co-resident CTA hides the prologue /
-// epilogue latencies that dominate when there are only one or two KV blocks (cross-attention: 77 / 16 keys).
-template <int G>
+// G = Q tiles per CTA.  G = 1 (256 TMEM columns, 66-98 KB smem, two CTAs per SM) is what runs: the co-resident CTA
+// hides the prologue / epilogue latencies.  G = 2 (one CTA per SM, the two tiles share every K/V load) is kept for
+// measurements (OMG_ATTN_TILES=2); since P moved to TMEM the shared K/V load no longer pays for the lock-step.
+template <int G, int KV_STAGES_>
 struct AttCfg {
     static constexpr int THREADS = 128 + 128 * G;  // warpgroup 0: TMA + MMA issuer warps, then one softmax warpgroup per tile
-    static constexpr int KV_STAGES = G == 2 ? 6 : 3;
+    static constexpr int KV_STAGES = KV_STAGES_;
     static constexpr int SMEM = 1024 + G * ATT_Q_BYTES + KV_STAGES * 2 * ATT_K_BYTES + 512;
     static constexpr int TMEM_COLS = G == 2 ? 512 : 256;
     static constexpr int O_COL0 = G * 2 * 64;      // S_g[b] at (g*2+b)*64, O_g at O_COL0 + g*64
@@ -78,9 +78,10 @@ struct alignas(64) AttnParams {
 //   softmax:  read S_g[b], (rare) rescale O_g, P = exp2(S*scale - m), P_g[b] -> TMEM (fp16 pairs)  ->  p_full[g][b]
 //   MMA:      S_g[b] = Q_g K_{j+2}^T ; O_g += P_g[b] V_j  ->  p_empty[g][b]
 // S and P are double-buffered, so the softmax warps never wait for the tensor core in steady state and vice versa.
-template <int G>
-__global__ void __launch_bounds__(AttCfg<G>::THREADS, G == 1 ? 2 : 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
-    constexpr int ATT_KV_STAGES = AttCfg<G>::KV_STAGES;
+template <int G, int KVS>
+__global__ void __launch_bounds__(AttCfg<G, KVS>::THREADS, G == 1 ? 2 : 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
+    using Cfg = AttCfg<G, KVS>;
+    constexpr int ATT_KV_STAGES = KVS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* q_smem = smem;                                          // G x 16 KB
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(AttCfg<G>::THREADS, G == 1 ? 2 : 1) attn_tc_ke
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, AttCfg<G>::TMEM_COLS);
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -161,8 +162,8 @@ __global__ void __launch_bounds__(AttCfg<G>::THREADS, G == 1 ? 2 : 1) attn_tc_ke
             const uint64_t q_desc = umma_desc_sw128(smem_u32(q_smem + g * ATT_Q_BYTES), 1024, 16);
             const uint64_t k_desc0 = umma_desc_sw128(smem_u32(kv_smem), 1024, 16);
             const uint64_t v_desc0 = umma_desc_sw128(smem_u32(kv_smem + ATT_K_BYTES), 1024, 1024);
-            const uint32_t p_tmem_g = tmem_base + AttCfg<G>::P_COL0 + g * 64;
-            const uint32_t o_tmem_g = tmem_base + AttCfg<G>::O_COL0 + g * 64;
+            const uint32_t p_tmem_g = tmem_base + Cfg::P_COL0 + g * 64;
+            const uint32_t o_tmem_g = tmem_base + Cfg::O_COL0 + g * 64;
             auto issue_s = [&](int jb) {  // scores of block jb into S_g[jb & 1]
                 const uint64_t kd = k_desc0 + (uint64_t)((jb % ATT_KV_STAGES) * ((2 * ATT_K_BYTES) >> 4));
 #pragma unroll
@@ -208,8 +209,8 @@ __global__ void __launch_bounds__(AttCfg<G>::THREADS, G == 1 ? 2 : 1) attn_tc_ke
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t s_tmem = tmem_base + g * 128 + lane_base;
-        const uint32_t o_tmem = tmem_base + AttCfg<G>::O_COL0 + g * 64 + lane_base;
-        const uint32_t p_tmem = tmem_base + AttCfg<G>::P_COL0 + g * 64 + lane_base;
+        const uint32_t o_tmem = tmem_base + Cfg::O_COL0 + g * 64 + lane_base;
+        const uint32_t p_tmem = tmem_base + Cfg::P_COL0 + g * 64 + lane_base;
         float m = -INFINITY, l = 0.f;
         constexpr float kRescaleThreshold = 8.0f;  // log2 domain: P may reach 2^8 before O is rescaled
 
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(AttCfg<G>::THREADS, G == 1 ? 2 : 1) attn_tc_ke
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, AttCfg<G>::TMEM_COLS);
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 static int make_attn_map(CUtensorMap* m, const void* ptr, int cols, int ld, int tokens, long long bs, int nb,
@@ -367,8 +368,9 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
     static bool configured = false;
     static int force_g = 0;
     if (!configured) {
-        OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
-        OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2>::SMEM));
+        OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1, 3>::SMEM));
+        OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1, 5>::SMEM));
+        OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2, 6>::SMEM));
         const char* e = getenv("OMG_ATTN_TILES");  // 1 | 2: force the tiles-per-CTA variant (measurements)
         force_g = e ? atoi(e) : 0;
         configured = true;
@@ -405,14 +407,20 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
     p.scale_log2 = d->scale * 1.4426950408889634f;
     p.out_weight = d->out_weight;
     p.accumulate = d->accumulate;
-    // short key sequences (cross-attention) are latency-bound: single-tile CTAs, two per SM
-    const int tiles = force_g ? force_g : (d->n_kv <= 2 * ATT_BKV ? 1 : 2);
+    // Single-tile CTAs, two per SM, for every shape: two independent CTAs overlap each other's prologue / epilogue
+    // with the other's main loop, which the two-tile CTA (tiles start and end together) cannot (measured, 5 KV
+    // stages each: 604 vs 569 TFLOP/s at N = 4096, 388 vs 362 at N = 1024).  Short key sequences (cross-attention,
+    // one or two KV blocks) take the 3-stage variant: less shared memory to set up per CTA.
+    const int tiles = force_g ? force_g : 1;
     if (tiles == 1) {
         dim3 grid((d->n_q + ATT_BQ - 1) / ATT_BQ, d->heads, d->n_items);
-        OMG_CUDA(launch_pdl(attn_tc_kernel<1>, grid, dim3(AttCfg<1>::THREADS), AttCfg<1>::SMEM, stream, p));
+        if (d->n_kv <= 2 * ATT_BKV)
+            OMG_CUDA(launch_pdl(attn_tc_kernel<1, 3>, grid, dim3(AttCfg<1, 3>::THREADS), AttCfg<1, 3>::SMEM, stream, p));
+        else
+            OMG_CUDA(launch_pdl(attn_tc_kernel<1, 5>, grid, dim3(AttCfg<1, 5>::THREADS), AttCfg<1, 5>::SMEM, stream, p));
     } else {
         dim3 grid((d->n_q + 2 * ATT_BQ - 1) / (2 * ATT_BQ), d->heads, d->n_items);
-        OMG_CUDA(launch_pdl(attn_tc_kernel<2>, grid, dim3(AttCfg<2>::THREADS), AttCfg<2>::SMEM, stream, p));
+        OMG_CUDA(launch_pdl(attn_tc_kernel<2, 6>, grid, dim3(AttCfg<2, 6>::THREADS), AttCfg<2, 6>::SMEM, stream, p));
     }
     return check_launch("attn_tc_kernel");
 }
