@@ -384,9 +384,10 @@ def _main():
             wl.pipe.dedup = False
             out["effective"] = {"value": args.steps / (ms_eff / 1e3), "unit": "images/sec",
                                 "sample_forwards_per_image": 172, "rel_l2_vs_as_executed": dedup_err,
-                                "note": "mathematically identical work de-duplicated (pipe.dedup=True; bitwise equal when "
-                                        "the tile shapes coincide, otherwise fp32 summation-order differences of the "
-                                        "B=2 vs B=4 launches); value/e2e above are as-executed (296 sample-forwards)"}
+                                "note": "mathematically identical work de-duplicated (pipe.dedup=True); the B=2 launches "
+                                        "use other tile shapes and skip the identity prompt-to-prompt edit, so latents "
+                                        "agree to fp16 rounding noise, bitwise on the test topology; value/e2e above "
+                                        "are as-executed (296 sample-forwards)"}
             # informational, outside the metric (which is defined on latents): the step after the loop
             # (lora_pipeline.py:634-661), both images of a stage decoded to 1024^2 by omg_b200.vae
             from omg_b200 import synthetic
