@@ -32,7 +32,7 @@ def draw_kps_multi(image_size, kps_list, color_list=((255, 0, 0), (0, 255, 0), (
             poly = cv2.ellipse2Poly((int(np.mean(xs)), int(np.mean(ys))), (int(length / 2), stick_width), int(angle),
                                     0, 360, 1)
             canvas = cv2.fillConvexPoly(canvas.copy(), poly, color)
-        canvas = (canvas * 0.6)
+        canvas = (canvas * 0.6).astype(np.uint8)  # truncation per face, as the reference does (:148)
         for idx, (x, y) in enumerate(kps):
             canvas = cv2.circle(canvas.copy(), (int(x), int(y)), 10, color_list[idx], -1)
     return canvas.astype(np.uint8)

@@ -7,6 +7,8 @@ Fixtures (all fp32, fixed seeds):
   p2p_edit.pt      AttentionReplace with a one-word edit and a partial cross_replace window (toy tokenizer).
   ip_attn.pt       IPAttnProcessor / IPAttnProcessor2_0 / AttnProcessor under a shim Attention module.
   resampler.pt     Resampler(dim=128, depth=2, heads=4, 16 queries, 512 -> 256).
+  kps.npz          draw_kps_multi (inference_instantid.py:127-156, extracted from the file by ast: the module itself
+                   imports diffusers) on three faces at 256 x 256.
 """
 import os
 import sys
@@ -140,7 +142,24 @@ def make_resampler():
     torch.save({"sd": r.state_dict(), "x": x, "y": y, "heads": 4, "dim_head": 32}, os.path.join(OUT, "resampler.pt"))
 
 
+def make_kps():
+    import ast
+    import math
+
+    import cv2
+    import numpy as np
+    import PIL.Image
+    src = open(os.path.join(REF, "inference_instantid.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "draw_kps_multi")
+    ns = {"np": np, "cv2": cv2, "math": math, "PIL": PIL}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "inference_instantid.py", "exec"), ns)
+    kps = [[[60 + d, 90], [110 + d, 88], [86 + d, 120], [66 + d, 150], [108 + d, 148]] for d in (0, 70, 120)]
+    img = np.asarray(ns["draw_kps_multi"](PIL.Image.new("RGB", (256, 256)), kps))
+    np.savez_compressed(os.path.join(OUT, "kps.npz"), kps=np.array(kps), image=img)
+
+
 if __name__ == "__main__":
+    make_kps()
     make_p2p()
     make_ip()
     make_resampler()

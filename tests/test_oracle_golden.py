@@ -115,3 +115,19 @@ def test_euler_schedule_known_values():
     eps = torch.randn(2, 4, 8, 8)
     y = s.step(eps, 3, x)
     assert torch.allclose(y, x + eps * (s.sigmas[4] - s.sigmas[3]), atol=1e-5)
+
+
+def test_draw_kps_multi_matches_the_reference_function():
+    """IdentityNet condition image (inference_instantid.py:127-156): the CLI's renderer vs the golden image produced
+    by the reference's own function on three faces (truncation to uint8 after each face included)."""
+    import importlib.util
+    import numpy as np
+    pytest.importorskip("cv2")
+    spec = importlib.util.spec_from_file_location(
+        "omg_cli_instantid", os.path.join(os.path.dirname(__file__), "..", "inference_instantid.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "kps.npz"))
+    got = cli.draw_kps_multi((256, 256), d["kps"].tolist())
+    assert got.dtype == np.uint8 and got.shape == (256, 256, 3)
+    assert np.array_equal(got, d["image"])
