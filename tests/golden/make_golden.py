@@ -7,6 +7,9 @@ Fixtures (all fp32, fixed seeds):
   p2p_edit.pt      AttentionReplace with a one-word edit and a partial cross_replace window (toy tokenizer).
   ip_attn.pt       IPAttnProcessor / IPAttnProcessor2_0 / AttnProcessor under a shim Attention module.
   resampler.pt     Resampler(dim=128, depth=2, heads=4, 16 queries, 512 -> 256).
+  cli.pt           prepare_text of both CLIs (inference_lora.py:128-149, inference_instantid.py:233-254) and
+                   LoraMultiConceptPipeline.get_region_mask (src/pipelines/lora_pipeline.py:673-681), each extracted from
+                   its file by ast (the modules import diffusers) and run on fixed inputs.
   kps.npz          draw_kps_multi (inference_instantid.py:127-156, extracted from the file by ast: the module itself
                    imports diffusers) on three faces at 256 x 256.
 """
@@ -158,7 +161,39 @@ def make_kps():
     np.savez_compressed(os.path.join(OUT, "kps.npz"), kps=np.array(kps), image=img)
 
 
+def _extract(path, name, cls=None):
+    import ast
+    tree = ast.parse(open(os.path.join(REF, path)).read())
+    body = tree.body
+    if cls is not None:
+        body = next(n for n in body if isinstance(n, ast.ClassDef) and n.name == cls).body
+    fn = next(n for n in body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"torch": torch, "F": torch.nn.functional}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
+def make_cli():
+    lora_pt = _extract("inference_lora.py", "prepare_text")
+    iid_pt = _extract("inference_instantid.py", "prepare_text")
+    region_mask = _extract("src/pipelines/lora_pipeline.py", "get_region_mask", cls="LoraMultiConceptPipeline")
+    lora_in = ["[a man, smiling]-*-[blurry, ugly]|[a woman [with] hat]-*-[noisy]", "[only one]-*-[neg]|", ""]
+    iid_in = ["[a man]-*-[blurry]-*-./a.jpg|[a woman]-*-[noisy]-*-./b.png", ""]
+    g = torch.Generator().manual_seed(0)
+    masks = []
+    for shape in ((64, 64), (64, 64), (48, 80)):
+        m = (torch.rand(shape, generator=g) > 0.6).float()
+        m[: shape[0] // 4] = 0.5  # non-binary values are NOT part of a region (mask == 1, lora_pipeline.py:680)
+        masks.append(m)
+    cases = [([masks[0], None, masks[1]], 8, 8), ([masks[2]], 6, 10), ([None, None], 8, 8)]
+    out = {"lora_prepare_text": [(s, lora_pt("P", s)) for s in lora_in],
+           "instantid_prepare_text": [(s, iid_pt("P", s)) for s in iid_in],
+           "region_mask": [{"masks": ml, "h": h, "w": w, "out": region_mask(None, ml, h, w)} for ml, h, w in cases]}
+    torch.save(out, os.path.join(OUT, "cli.pt"))
+
+
 if __name__ == "__main__":
+    make_cli()
     make_kps()
     make_p2p()
     make_ip()

@@ -131,3 +131,34 @@ def test_draw_kps_multi_matches_the_reference_function():
     got = cli.draw_kps_multi((256, 256), d["kps"].tolist())
     assert got.dtype == np.uint8 and got.shape == (256, 256, 3)
     assert np.array_equal(got, d["image"])
+
+
+def _load_cli(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("omg_cli_" + name, os.path.join(os.path.dirname(__file__), "..", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_cli_prepare_text_and_region_mask_match_the_reference_functions():
+    """prepare_text of both CLIs and the union-of-regions mask (lora_pipeline.py:673-681) against the outputs of the
+    reference's own functions; the product computes the union from the per-concept binary latent masks."""
+    from omg_b200.pipelines import _binary_latent_mask
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "cli.pt"))
+    lora_cli, iid_cli = _load_cli("inference_lora"), _load_cli("inference_instantid")
+    for s, want in gold["lora_prepare_text"]:
+        assert lora_cli.prepare_text("P", s) == want
+    for s, want in gold["instantid_prepare_text"]:
+        assert iid_cli.prepare_text("P", s) == want
+    for case in gold["region_mask"]:
+        union = torch.zeros(case["h"], case["w"])
+        for m in case["masks"]:
+            b = _binary_latent_mask(m, case["h"], case["w"], "cpu")
+            if b is not None:
+                union = torch.maximum(union, b.reshape(case["h"], case["w"]).float())
+        assert torch.equal(union, case["out"].float())
+    # the oracle's own restatement of the same function
+    from oracle.pipeline import get_region_mask as oracle_region_mask
+    for case in gold["region_mask"]:
+        assert torch.equal(oracle_region_mask(case["masks"], case["h"], case["w"]).float(), case["out"].float())
