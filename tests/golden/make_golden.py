@@ -10,6 +10,9 @@ Fixtures (all fp32, fixed seeds):
   cli.pt           prepare_text of both CLIs (inference_lora.py:128-149, inference_instantid.py:233-254) and
                    LoraMultiConceptPipeline.get_region_mask (src/pipelines/lora_pipeline.py:673-681), each extracted from
                    its file by ast (the modules import diffusers) and run on fixed inputs.
+  fusion.pt        the region noise-fusion + classifier-free-guidance statements of LoraMultiConceptPipeline.__call__
+                   (src/pipelines/lora_pipeline.py:568-612): the two `if` nodes are cut out of the method's AST and
+                   executed unmodified against stub objects (concept UNet returning prepared noise, adapter-switch log).
   kps.npz          draw_kps_multi (inference_instantid.py:127-156, extracted from the file by ast: the module itself
                    imports diffusers) on three faces at 256 x 256.
 """
@@ -173,6 +176,60 @@ def _extract(path, name, cls=None):
     return ns[name]
 
 
+def make_fusion():
+    """Execute the reference's own fusion statements: three concepts, one of them without a mask (skipped), two with
+    overlapping masks (sum in the overlap), one mask with non-binary values."""
+    import ast
+    import types
+    path = "src/pipelines/lora_pipeline.py"
+    tree = ast.parse(open(os.path.join(REF, path)).read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "LoraMultiConceptPipeline")
+    call = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "__call__")
+    nodes = []
+    for n in ast.walk(call):
+        if isinstance(n, ast.If):
+            src = ast.unparse(n.test)
+            if src == "i > 15 and stage == 2" or src == "self.do_classifier_free_guidance":
+                nodes.append(n)
+    fuse_if = next(n for n in nodes if ast.unparse(n.test).startswith("i > 15"))
+    cfg_if = [n for n in nodes if ast.unparse(n.test) == "self.do_classifier_free_guidance"
+              and "noise_pred.chunk" in ast.unparse(n)][0]
+    code = compile(ast.Module(body=[fuse_if, cfg_if], type_ignores=[]), path, "exec")
+    region_mask = _extract(path, "get_region_mask", cls="LoraMultiConceptPipeline")
+    g = torch.Generator().manual_seed(3)
+    h, w, H, W = 16, 24, 64, 96
+    noise_pred = torch.randn(4, 4, h, w, generator=g).half().float()   # fp16-representable: the CUDA path stores fp16
+    latent_model_input = torch.randn(4, 4, h, w, generator=g).half().float()
+    m0 = torch.zeros(H, W)
+    m0[8:48, 4:52] = 1
+    m1 = torch.zeros(H, W)
+    m1[20:60, 40:88] = 1
+    m1[20:24] *= 0.5          # non-binary stripe: not part of the region (== 1 tests)
+    mask_list = [m0, None, m1]
+    region_noise = [torch.randn(2, 4, h, w, generator=g).half().float() for _ in range(3)]
+    log = {"adapters": [], "unet_inputs": []}
+    calls = iter([region_noise[0], region_noise[2]])  # the concept without a mask never runs
+
+    def unet(sample, t, encoder_hidden_states=None, cross_attention_kwargs=None, added_cond_kwargs=None, return_dict=False):
+        log["unet_inputs"].append((sample.clone(), float(t), dict(cross_attention_kwargs)))
+        return (next(calls),)
+
+    concept_models = types.SimpleNamespace(_execution_device="cpu", unet=unet,
+                                           set_adapters=lambda *a, **k: log["adapters"].append((a, k)))
+    self_stub = types.SimpleNamespace(do_classifier_free_guidance=True,
+                                      get_region_mask=lambda ml, fh, fw: region_mask(None, ml, fh, fw))
+    ns = {"torch": torch, "F": torch.nn.functional, "self": self_stub, "i": 16, "stage": 2, "t": 499.0,
+          "noise_pred": noise_pred.clone(), "mask_list": mask_list, "latent_model_input": latent_model_input,
+          "region_prompt_embeds_list": [None] * 3, "region_add_text_embeds_list": [None] * 3,
+          "add_time_ids_list": [None] * 3, "region_prompts": ["a", "b", "c"], "lora_list": ["A", "B", "C"],
+          "styleL": True, "concept_models": concept_models, "guidance_scale": 7.5}
+    exec(code, ns)
+    torch.save({"noise_pred_in": noise_pred, "latent_model_input": latent_model_input, "masks": mask_list,
+                "region_noise": region_noise, "guidance_scale": 7.5, "noise_after_cfg": ns["noise_pred"],
+                "new_noise_pred": ns["new_noise_pred"], "adapters": log["adapters"],
+                "unet_inputs": log["unet_inputs"]}, os.path.join(OUT, "fusion.pt"))
+
+
 def make_cli():
     lora_pt = _extract("inference_lora.py", "prepare_text")
     iid_pt = _extract("inference_instantid.py", "prepare_text")
@@ -193,6 +250,7 @@ def make_cli():
 
 
 if __name__ == "__main__":
+    make_fusion()
     make_cli()
     make_kps()
     make_p2p()

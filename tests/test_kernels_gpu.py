@@ -345,3 +345,38 @@ def test_tall_tiles_conv_rowvec_and_stats(ops):
     s = stats.sum(0)
     assert torch.allclose(s[:, 0], href.sum(1), rtol=2e-3, atol=2e-2)
     assert torch.allclose(s[:, 1], (href * href).sum(1), rtol=3e-3, atol=2e-2)
+
+
+@pytest.mark.xfail(strict=False, reason="written after round 1's GPU minutes were spent: not yet executed on a B200 "
+                   "(the oracle side of the same golden is checked on CPU in test_oracle_golden.py); drop the mark "
+                   "once it has run")
+def test_fuse_step_matches_the_reference_fusion_statements(ops):
+    """omg_fuse_step against tests/golden/fusion.pt: the output of the reference's own fusion + guidance statements
+    (lora_pipeline.py:568-612, executed from the method's AST): one concept without a mask (skipped), two overlapping
+    masks, a non-binary stripe in one mask.  The Euler update on top is x + eps * (sigma_next - sigma)."""
+    import os
+    from omg_b200.pipelines import _binary_latent_mask
+    d = torch.load(os.path.join(os.path.dirname(__file__), "golden", "fusion.pt"))
+    n_in = d["noise_pred_in"]
+    h, w = n_in.shape[2], n_in.shape[3]
+    HW = h * w
+
+    def nhwc8(x):
+        t = torch.zeros(x.shape[0], HW, 8, device="cuda", dtype=torch.float16)
+        t[..., :4] = x.permute(0, 2, 3, 1).reshape(x.shape[0], HW, 4).half().cuda()
+        return t
+
+    active = [k for k, m in enumerate(d["masks"]) if m is not None]
+    assert active == [0, 2]
+    nm = nhwc8(n_in)
+    ncs = [nhwc8(d["region_noise"][k]) for k in active]
+    masks = [_binary_latent_mask(d["masks"][k], h, w, "cuda") for k in active]
+    lat0 = (torch.randn(2, HW, 4, generator=torch.Generator().manual_seed(1)) * 10).cuda()
+    lat = lat0.clone()
+    nxt = torch.empty(4, HW, 8, device="cuda", dtype=torch.float16)
+    nxc = torch.empty(2, HW, 8, device="cuda", dtype=torch.float16)
+    sig, sign = 5.0, 4.2
+    ops.fuse_step(nm, ncs, masks, d["guidance_scale"], sig, sign, lat, nxt, nxc)
+    eps = d["noise_after_cfg"].permute(0, 2, 3, 1).reshape(2, HW, 4).cuda()
+    ref = lat0 + eps * (sign - sig)
+    assert rel(lat, ref) < 1e-5

@@ -162,3 +162,19 @@ def test_cli_prepare_text_and_region_mask_match_the_reference_functions():
     from oracle.pipeline import get_region_mask as oracle_region_mask
     for case in gold["region_mask"]:
         assert torch.equal(oracle_region_mask(case["masks"], case["h"], case["w"]).float(), case["out"].float())
+
+
+def test_noise_fusion_matches_the_reference_statements():
+    """oracle.pipeline.fuse_noise + CFG against the output of the reference's own fusion / guidance statements
+    (lora_pipeline.py:568-612, executed from the method's AST by make_golden.py): a concept without a mask is skipped,
+    overlapping masks add up, non-binary mask values are outside the region."""
+    from oracle.pipeline import fuse_noise
+    d = torch.load(os.path.join(os.path.dirname(__file__), "golden", "fusion.pt"))
+    fused = fuse_noise(d["noise_pred_in"], d["region_noise"], d["masks"])
+    assert torch.equal(fused[[1, 3]], d["new_noise_pred"])
+    nu, nt = fused.chunk(2)
+    assert torch.allclose(nu + d["guidance_scale"] * (nt - nu), d["noise_after_cfg"], rtol=0, atol=1e-6)
+    # what the concept UNets were fed: image 1's scaled latent twice, adapters [concept, style] at [0.7, 0.5]
+    for sample, t, kw in d["unet_inputs"]:
+        assert torch.equal(sample, torch.cat([d["latent_model_input"][3:4]] * 2)) and kw == {"scale": 0.8}
+    assert [a[0][0] for a in d["adapters"]] == [["A", "style"], ["C", "style"]]
