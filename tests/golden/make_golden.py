@@ -10,6 +10,9 @@ Fixtures (all fp32, fixed seeds):
   cli.pt           prepare_text of both CLIs (inference_lora.py:128-149, inference_instantid.py:233-254) and
                    LoraMultiConceptPipeline.get_region_mask (src/pipelines/lora_pipeline.py:673-681), each extracted from
                    its file by ast (the modules import diffusers) and run on fixed inputs.
+  region_attn.pt   RegionControlNet_AttnProcessor (src/pipelines/lora_pipeline.py:61-133; the class is cut out of the
+                   module by ast, the module imports diffusers) driven by the reference's own AttentionReplace on a shim
+                   Attention: self / cross layers, inside / outside the replace windows, identical and edited prompts.
   fusion.pt        the region noise-fusion + classifier-free-guidance statements of LoraMultiConceptPipeline.__call__
                    (src/pipelines/lora_pipeline.py:568-612): the two `if` nodes are cut out of the method's AST and
                    executed unmodified against stub objects (concept UNet returning prepared noise, adapter-switch log).
@@ -176,6 +179,51 @@ def _extract(path, name, cls=None):
     return ns[name]
 
 
+REGION_CASES = [(False, False, 0), (False, False, 5), (False, True, 1), (False, True, 7),
+                (True, False, 0), (True, False, 5), (True, True, 1), (True, True, 7)]  # (edit, is_cross, step)
+
+
+def region_case_setup(edit):
+    prompts = ["a photo of a man on the beach", "a photo of a dog on the beach"] if edit else ["a b c"] * 2
+    cross = {"default_": 0.6, "dog": (0.2, 0.9)} if edit else {"default_": 1.0}
+    return prompts, cross
+
+
+def region_case_inputs(idx, is_cross, dim=64, ctx_dim=32, n=16):
+    """Inputs of case idx, regenerated from the seed by the tests (keeps the fixture small)."""
+    gen = torch.Generator().manual_seed(100 + idx)
+    x = torch.randn(4, n, dim, generator=gen)
+    ctx = torch.randn(4, 77, ctx_dim, generator=gen) if is_cross else None
+    return x, ctx
+
+
+def make_region_attn():
+    import ast
+    from typing import Optional
+    from src.prompt_attention.p2p_attention import AttentionReplace
+    path = "src/pipelines/lora_pipeline.py"
+    tree = ast.parse(open(os.path.join(REF, path)).read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "RegionControlNet_AttnProcessor")
+    ns = {"torch": torch, "Optional": Optional, "USE_PEFT_BACKEND": True}
+    exec(compile(ast.Module(body=[cls], type_ignores=[]), path, "exec"), ns)
+    Proc = ns["RegionControlNet_AttnProcessor"]
+    dim, ctx_dim, heads = 64, 32, 2
+    torch.manual_seed(7)
+    attn_self, attn_cross = ShimAttention(dim, dim, heads), ShimAttention(dim, ctx_dim, heads)
+    out = {"dim": dim, "ctx_dim": ctx_dim, "heads": heads, "attn_self": attn_self.state_dict(),
+           "attn_cross": attn_cross.state_dict(), "cases": []}
+    for idx, (edit, is_cross, step) in enumerate(REGION_CASES):
+        prompts, cross = region_case_setup(edit)
+        x, ctx = region_case_inputs(idx, is_cross, dim, ctx_dim)
+        c = AttentionReplace(prompts, 10, dict(cross), 0.3, tokenizer=ToyTokenizer(), width=4, height=4)
+        c.num_att_layers = 2
+        c.cur_step = step
+        with torch.no_grad():
+            y = Proc(controller=c, place_in_unet="mid")(attn_cross if is_cross else attn_self, x, ctx)
+        out["cases"].append({"edit": edit, "is_cross": is_cross, "step": step, "y": y, "cur_att_layer": c.cur_att_layer})
+    torch.save(out, os.path.join(OUT, "region_attn.pt"))
+
+
 def make_fusion():
     """Execute the reference's own fusion statements: three concepts, one of them without a mask (skipped), two with
     overlapping masks (sum in the overlap), one mask with non-binary values."""
@@ -250,6 +298,7 @@ def make_cli():
 
 
 if __name__ == "__main__":
+    make_region_attn()
     make_fusion()
     make_cli()
     make_kps()

@@ -178,3 +178,30 @@ def test_noise_fusion_matches_the_reference_statements():
     for sample, t, kw in d["unet_inputs"]:
         assert torch.equal(sample, torch.cat([d["latent_model_input"][3:4]] * 2)) and kw == {"scale": 0.8}
     assert [a[0][0] for a in d["adapters"]] == [["A", "style"], ["C", "style"]]
+
+
+def test_region_processor_restatement_matches_the_reference_class():
+    """RegionControlNet_AttnProcessor (lora_pipeline.py:61-133) + the reference's AttentionReplace, run from the
+    reference source (tests/golden/region_attn.pt), against the fp32 restatement that the GPU test of
+    omg_b200.processors.FusedRegionAttnProcessor uses as its expectation (materialised probabilities through the oracle
+    controller).  Closes the chain reference class == restatement (here) ~= fused CUDA processor (test_processors_gpu)."""
+    from make_golden import REGION_CASES, ShimAttention, region_case_inputs, region_case_setup
+    d = torch.load(os.path.join(os.path.dirname(__file__), "golden", "region_attn.pt"))
+    assert len(d["cases"]) == len(REGION_CASES)
+    for idx, case in enumerate(d["cases"]):
+        edit, is_cross, step = case["edit"], case["is_cross"], case["step"]
+        assert (edit, is_cross, step) == REGION_CASES[idx]
+        prompts, cross = region_case_setup(edit)
+        x, ctx = region_case_inputs(idx, is_cross, d["dim"], d["ctx_dim"])
+        a = ShimAttention(d["dim"], d["ctx_dim"] if is_cross else d["dim"], d["heads"])
+        a.load_state_dict(d["attn_cross"] if is_cross else d["attn_self"])
+        oc = p2p.AttentionReplaceOracle(prompts, 10, dict(cross), 0.3, 4, 4, tokenizer=ToyTokenizer())
+        oc.num_att_layers, oc.cur_step = 2, step
+        src = ctx if is_cross else x
+        with torch.no_grad():
+            q, k, v = a.to_q(x), a.to_k(src), a.to_v(src)
+            pr = a.get_attention_scores(a.head_to_batch_dim(q), a.head_to_batch_dim(k))
+            pr = oc(pr, is_cross, "mid")
+            y = a.to_out[0](a.batch_to_head_dim(torch.bmm(pr, a.head_to_batch_dim(v))))
+        assert oc.cur_att_layer == case["cur_att_layer"]
+        assert torch.allclose(y, case["y"], rtol=0, atol=2e-6), (idx, float((y - case["y"]).abs().max()))
