@@ -55,6 +55,27 @@ def fuse_noise(noise_pred, region_noises, mask_list):
     return out
 
 
+def concept_noises(lmi, t, concepts, identitynet=None, identity_cond=None, identity_scale: float = 1.0):
+    """One noise prediction per concept with a mask (None for the others): the concept loop of lora_pipeline.py:576-599
+    / instantid_pipeline.py:626-672.  Every concept sees image 1's scaled latent twice; InstantID concepts run the
+    IdentityNet on the face tokens alone and the UNet on [text tokens | face tokens]."""
+    region_noises = []
+    for c in concepts:
+        if c.mask is None:
+            region_noises.append(None)
+            continue
+        rl = torch.cat([lmi[3:4].clone()] * 2)                         # :583-585
+        ctx = c.prompt_embeds
+        rdown = rmid = None
+        if identitynet is not None:                                    # instantid_pipeline.py:638-663
+            rdown, rmid = controlnet_forward(identitynet, rl, t, c.image_tokens, identity_cond, identity_scale,
+                                             c.add_text_embeds, c.add_time_ids)
+        if c.image_tokens is not None:
+            ctx = torch.cat([c.prompt_embeds, c.image_tokens], dim=1)
+        region_noises.append(unet_forward(c.unet, rl, t, ctx, c.add_text_embeds, c.add_time_ids, rdown, rmid))
+    return region_noises
+
+
 def denoise(main: Ctx, latents_1: torch.Tensor, prompt_embeds, add_text_embeds, add_time_ids,
             concepts: List[Concept], stage: int, num_inference_steps: int, guidance_scale: float,
             controlnet: Optional[Ctx] = None, controlnet_cond=None, controlnet_scale: float = 1.0,
@@ -76,22 +97,8 @@ def denoise(main: Ctx, latents_1: torch.Tensor, prompt_embeds, add_text_embeds, 
                                            add_text_embeds, add_time_ids)
         noise_pred = unet_forward(main, lmi, t, prompt_embeds, add_text_embeds, add_time_ids, down, mid)
         if i > fusion_after_step and stage == 2:                       # :568
-            mask_list = [c.mask for c in concepts]
-            region_noises = []
-            for c in concepts:
-                if c.mask is None:
-                    region_noises.append(None)
-                    continue
-                rl = torch.cat([lmi[3:4].clone()] * 2)                 # :583-585
-                ctx = c.prompt_embeds
-                rdown = rmid = None
-                if identitynet is not None:                            # instantid_pipeline.py:638-663
-                    rdown, rmid = controlnet_forward(identitynet, rl, t, c.image_tokens, identity_cond,
-                                                     identity_scale, c.add_text_embeds, c.add_time_ids)
-                if c.image_tokens is not None:
-                    ctx = torch.cat([c.prompt_embeds, c.image_tokens], dim=1)
-                region_noises.append(unet_forward(c.unet, rl, t, ctx, c.add_text_embeds, c.add_time_ids, rdown, rmid))
-            noise_pred = fuse_noise(noise_pred, region_noises, mask_list)
+            region_noises = concept_noises(lmi, t, concepts, identitynet, identity_cond, identity_scale)
+            noise_pred = fuse_noise(noise_pred, region_noises, [c.mask for c in concepts])
         nu, nt = noise_pred.chunk(2)                                    # :610-612
         guided = nu + guidance_scale * (nt - nu)
         latents = sched.step(guided, i, latents)                       # :615

@@ -16,6 +16,9 @@ Fixtures (all fp32, fixed seeds):
   fusion.pt        the region noise-fusion + classifier-free-guidance statements of LoraMultiConceptPipeline.__call__
                    (src/pipelines/lora_pipeline.py:568-612): the two `if` nodes are cut out of the method's AST and
                    executed unmodified against stub objects (concept UNet returning prepared noise, adapter-switch log).
+  fusion_iid.pt    the same statements of InstantidMultiConceptPipeline.__call__ (src/pipelines/instantid_pipeline.py:
+                   618-686): every call the block makes to the IdentityNet and to the concept UNet is recorded
+                   (inputs, face / text tokens, condition image, scale, residual hand-over), plus the fused noise.
   kps.npz          draw_kps_multi (inference_instantid.py:127-156, extracted from the file by ast: the module itself
                    imports diffusers) on three faces at 256 x 256.
 """
@@ -278,6 +281,74 @@ def make_fusion():
                 "unet_inputs": log["unet_inputs"]}, os.path.join(OUT, "fusion.pt"))
 
 
+def make_fusion_instantid():
+    import ast
+    import types
+    path = "src/pipelines/instantid_pipeline.py"
+    tree = ast.parse(open(os.path.join(REF, path)).read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "InstantidMultiConceptPipeline")
+    call = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "__call__")
+    ifs = [n for n in ast.walk(call) if isinstance(n, ast.If)]
+    fuse_if = next(n for n in ifs if ast.unparse(n.test) == "i > 15 and stage == 2")
+    cfg_if = next(n for n in ifs if ast.unparse(n.test) == "self.do_classifier_free_guidance"
+                  and "noise_pred.chunk" in ast.unparse(n))
+    code = compile(ast.Module(body=[fuse_if, cfg_if], type_ignores=[]), path, "exec")
+    region_mask = _extract(path, "get_region_mask", cls="InstantidMultiConceptPipeline")
+    g = torch.Generator().manual_seed(11)
+
+    def rn(*s):
+        return torch.randn(*s, generator=g)
+
+    h, w, H, W, D, P = 4, 6, 16, 24, 8, 8
+    noise_pred, lmi = rn(4, 4, h, w), rn(4, 4, h, w)
+    m0 = torch.zeros(H, W)
+    m0[2:14, 1:11] = 1
+    m1 = torch.zeros(H, W)
+    m1[4:15, 9:23] = 1
+    mask_list = [m0, None, m1]
+    text = [rn(2, 77, D) for _ in range(3)]
+    face = [rn(2, 16, D) for _ in range(3)]
+    pooled = [rn(2, P) for _ in range(3)]
+    tids = [rn(2, 6) for _ in range(3)]
+    cond = rn(2, 3, 8 * h, 8 * w)
+    cn_out = [([rn(2, 3, h, w), rn(2, 5, h // 2, w // 2)], rn(2, 7, h // 4, w // 4)) for _ in range(2)]
+    un_out = [rn(2, 4, h, w) for _ in range(2)]
+    log = {"controlnet": [], "unet": []}
+    cn_it, un_it = iter(cn_out), iter(un_out)
+
+    def controlnet(sample, t, encoder_hidden_states=None, controlnet_cond=None, conditioning_scale=None,
+                   guess_mode=None, added_cond_kwargs=None, return_dict=False):
+        log["controlnet"].append({"sample": sample.clone(), "t": float(t), "ctx": encoder_hidden_states.clone(),
+                                  "cond": controlnet_cond.clone(), "scale": conditioning_scale, "guess_mode": guess_mode,
+                                  "text_embeds": added_cond_kwargs["text_embeds"].clone(),
+                                  "time_ids": added_cond_kwargs["time_ids"].clone()})
+        return next(cn_it)
+
+    def unet(sample, t, encoder_hidden_states=None, cross_attention_kwargs=None, down_block_additional_residuals=None,
+             mid_block_additional_residual=None, added_cond_kwargs=None, return_dict=False):
+        log["unet"].append({"sample": sample.clone(), "t": float(t), "ctx": encoder_hidden_states.clone(),
+                            "cross_attention_kwargs": cross_attention_kwargs,
+                            "down": [d.clone() for d in down_block_additional_residuals],
+                            "mid": mid_block_additional_residual.clone(),
+                            "text_embeds": added_cond_kwargs["text_embeds"].clone(),
+                            "time_ids": added_cond_kwargs["time_ids"].clone()})
+        return (next(un_it),)
+
+    self_stub = types.SimpleNamespace(do_classifier_free_guidance=True, controlnet=controlnet,
+                                      get_region_mask=lambda ml, fh, fw: region_mask(None, ml, fh, fw))
+    ns = {"torch": torch, "F": torch.nn.functional, "self": self_stub, "i": 16, "stage": 2, "t": 433.0,
+          "noise_pred": noise_pred.clone(), "mask_list": mask_list, "latent_model_input": lmi,
+          "region_prompt_embeds_list": text, "region_add_text_embeds_list": pooled, "add_time_ids_list": tids,
+          "region_prompts": ["a", "b", "c"], "image_prompt_image_emb_list": face, "image": cond, "cond_scale": 0.8,
+          "guess_mode": False, "concept_models": types.SimpleNamespace(_execution_device="cpu", unet=unet),
+          "guidance_scale": 3.0}
+    exec(code, ns)
+    torch.save({"noise_pred_in": noise_pred, "latent_model_input": lmi, "masks": mask_list, "text": text, "face": face,
+                "pooled": pooled, "time_ids": tids, "cond": cond, "cond_scale": 0.8, "guidance_scale": 3.0, "t": 433.0,
+                "controlnet_out": cn_out, "unet_out": un_out, "controlnet_calls": log["controlnet"],
+                "unet_calls": log["unet"], "noise_after_cfg": ns["noise_pred"]}, os.path.join(OUT, "fusion_iid.pt"))
+
+
 def make_cli():
     lora_pt = _extract("inference_lora.py", "prepare_text")
     iid_pt = _extract("inference_instantid.py", "prepare_text")
@@ -298,6 +369,7 @@ def make_cli():
 
 
 if __name__ == "__main__":
+    make_fusion_instantid()
     make_region_attn()
     make_fusion()
     make_cli()

@@ -205,3 +205,45 @@ def test_region_processor_restatement_matches_the_reference_class():
             y = a.to_out[0](a.batch_to_head_dim(torch.bmm(pr, a.head_to_batch_dim(v))))
         assert oc.cur_att_layer == case["cur_att_layer"]
         assert torch.allclose(y, case["y"], rtol=0, atol=2e-6), (idx, float((y - case["y"]).abs().max()))
+
+
+def test_instantid_concept_pass_matches_the_reference_statements(monkeypatch):
+    """oracle.pipeline.concept_noises + fuse_noise + CFG against the reference's InstantID statements
+    (instantid_pipeline.py:618-686, executed from the method's AST): what the IdentityNet and the concept UNet are
+    called with - image 1's scaled latent twice, face tokens alone for the IdentityNet, [text | face] tokens for the
+    UNet, the shared condition image and scale, the residual hand-over - and the fused, guided noise."""
+    from oracle import pipeline as opipe
+    d = torch.load(os.path.join(os.path.dirname(__file__), "golden", "fusion_iid.pt"))
+    calls = {"cn": [], "un": []}
+    cn_it, un_it = iter(d["controlnet_out"]), iter(d["unet_out"])
+
+    def fake_controlnet(c, sample, t, ctx, cond, scale, text_embeds, time_ids):
+        calls["cn"].append(dict(c=c, sample=sample, t=float(t), ctx=ctx, cond=cond, scale=scale, text_embeds=text_embeds,
+                                time_ids=time_ids))
+        down, mid = next(cn_it)
+        return down, mid
+
+    def fake_unet(c, sample, t, ctx, text_embeds, time_ids, down=None, mid=None):
+        calls["un"].append(dict(c=c, sample=sample, t=float(t), ctx=ctx, text_embeds=text_embeds, time_ids=time_ids,
+                                down=down, mid=mid))
+        return next(un_it)
+
+    monkeypatch.setattr(opipe, "controlnet_forward", fake_controlnet)
+    monkeypatch.setattr(opipe, "unet_forward", fake_unet)
+    concepts = [opipe.Concept(prompt_embeds=d["text"][k], add_text_embeds=d["pooled"][k], add_time_ids=d["time_ids"][k],
+                              mask=d["masks"][k], unet=f"concept{k}", image_tokens=d["face"][k]) for k in range(3)]
+    noises = opipe.concept_noises(d["latent_model_input"], d["t"], concepts, identitynet="identitynet",
+                                  identity_cond=d["cond"], identity_scale=d["cond_scale"])
+    assert noises[1] is None and len(calls["cn"]) == len(d["controlnet_calls"]) == 2
+    for mine, ref in zip(calls["cn"], d["controlnet_calls"]):
+        assert mine["c"] == "identitynet" and mine["t"] == ref["t"] and mine["scale"] == ref["scale"]
+        for key in ("sample", "ctx", "cond", "text_embeds", "time_ids"):
+            assert torch.equal(mine[key], ref[key]), key
+    for k, (mine, ref) in enumerate(zip(calls["un"], d["unet_calls"])):
+        assert mine["c"] == ("concept0", "concept2")[k] and mine["t"] == ref["t"] and ref["cross_attention_kwargs"] is None
+        for key in ("sample", "ctx", "text_embeds", "time_ids", "mid"):
+            assert torch.equal(mine[key], ref[key]), key
+        assert all(torch.equal(a, b) for a, b in zip(mine["down"], ref["down"]))
+    fused = opipe.fuse_noise(d["noise_pred_in"], noises, d["masks"])
+    nu, nt = fused.chunk(2)
+    assert torch.allclose(nu + d["guidance_scale"] * (nt - nu), d["noise_after_cfg"], rtol=0, atol=1e-6)
