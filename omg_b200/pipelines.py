@@ -18,7 +18,7 @@ UNets (CUDA graphs)] -> omg_fuse_step.  No host sync happens inside the loop.
 import hashlib
 import os
 from dataclasses import dataclass
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, Optional, Tuple
 
 import torch
 

@@ -5,7 +5,7 @@ CFG, scheduler step), :674-681 (get_region_mask) and src/pipelines/instantid_pip
 concept pass runs IdentityNet + the IP-adapter UNet, the main pass may use a second ControlNet).  Text encoders,
 VAE, segmentation and face analysis are outside the hot path: prompt embeddings, masks and face tokens are inputs.
 """
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Callable, List, Optional
 
 import torch

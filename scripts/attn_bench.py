@@ -1,7 +1,6 @@
 import json, sys, torch
 sys.path.insert(0, ".")
 from omg_b200 import ops
-import torch.nn.functional as F
 dev = "cuda"
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 def timeit(fn, iters=10, warm=3):

@@ -2,7 +2,6 @@
 next to the torch library call (cuBLAS / cuDNN / SDPA) the reference would make.  Prints TFLOP/s and GB/s."""
 import json
 import sys
-import time
 
 import torch
 import torch.nn.functional as F

@@ -6,7 +6,6 @@
 Prints one JSON object per config; results are copied into BASELINE.md section 5.
 """
 import json
-import math
 import os
 import sys
 import time
@@ -14,12 +13,12 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from omg_b200 import factory, ops, synthetic  # noqa: E402
+from omg_b200 import synthetic  # noqa: E402
 from omg_b200.config import UNetConfig  # noqa: E402
 from omg_b200.pipelines import (ConceptModels, InstantidMultiConceptPipeline, LoraMultiConceptPipeline,  # noqa: E402
                                 revise_regionally_controlnet_forward)
 from omg_b200.prompt_attention import AttentionReplace  # noqa: E402
-from omg_b200.unet import PackedUNet, RowGroup, UNetRunner  # noqa: E402
+from omg_b200.unet import PackedUNet  # noqa: E402
 
 dev = "cuda"
 cfg = UNetConfig.sdxl()
