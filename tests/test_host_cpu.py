@@ -162,3 +162,20 @@ def test_data_parallel_plumbing_gloo_world2():
         assert a == [0.0, 1.0, 2.0, 3.0] and b == [0.0, 0.0, 0.0]      # rank 0's weights everywhere
         assert allv == [0.0, 1.0, 2.0, 3.0, 4.0]                       # image order restored
     assert res[0][4] == [0, 2, 4] and res[1][4] == [1, 3]
+
+
+def test_gemm_plan_tile_choice_is_host_logic_and_stable():
+    """omg_gemm_plan runs without a GPU: the wave-quantisation cost model behind the tile shape, and the number of
+    LayerNorm-statistics partials (2 per n-tile) every producer of one consumer must agree on.  N = 1280 / 640 / 320
+    (the narrow UNet widths) take 160-wide tiles (tall 256 x 160 at launch), the wide QKV / GEGLU GEMMs 256 (CTA pairs)."""
+    from omg_b200 import _lib as L
+    from omg_b200 import ops
+    assert ops.gemm_plan(1280, L.EPI_NONE, 4096) == (160, 16)      # main rows, c = 1280
+    assert ops.gemm_plan(1280, L.EPI_NONE, 8192) == (160, 16)      # grouped fusion step: same plan, so same partials
+    assert ops.gemm_plan(640, L.EPI_NONE, 16384) == (160, 8)
+    assert ops.gemm_plan(320, L.EPI_NONE, 65536) == (160, 4)
+    assert ops.gemm_plan(3840, L.EPI_NONE, 4096) == (256, 30)
+    assert ops.gemm_plan(10240, L.EPI_GEGLU, 4096) == (256, 80)
+    assert ops.gemm_plan(8, L.EPI_NONE, 65536)[0] == 64            # conv_out: 8 padded channels
+    with pytest.raises(RuntimeError):
+        ops.gemm_plan(4, L.EPI_NONE, 128)                          # N < 8 is rejected with an error string
