@@ -179,3 +179,34 @@ def test_gemm_plan_tile_choice_is_host_logic_and_stable():
     assert ops.gemm_plan(8, L.EPI_NONE, 65536)[0] == 64            # conv_out: 8 padded channels
     with pytest.raises(RuntimeError):
         ops.gemm_plan(4, L.EPI_NONE, 128)                          # N < 8 is rejected with an error string
+
+
+def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
+    """Every entry point validates its descriptor first and reports through the status code + omg_last_error(); none of
+    these calls reaches a CUDA API, so they run on a machine without a GPU (pointers are never dereferenced)."""
+    import ctypes as C
+    from omg_b200 import _lib as L
+    lib = L.load()
+    fake = C.c_void_p(0x1000)
+
+    def err(rc):
+        assert rc == 1
+        return lib.omg_last_error().decode()
+
+    assert "multiple of 8" in err(lib.omg_softmax_rows(fake, 4, 12, 16, 1.0, None))
+    assert "scale must be positive" in err(lib.omg_softmax_rows(fake, 4, 16, 16, -1.0, None))
+    d = L.AttnDesc()
+    d.head_dim, d.n_items = 32, 1
+    assert "head_dim 32 unsupported" in err(lib.omg_attention(C.byref(d), None))
+    d.head_dim, d.n_items = 64, 99
+    assert "n_items=99 out of range" in err(lib.omg_attention(C.byref(d), None))
+    assert "null descriptor" in err(lib.omg_gemm(None, None))
+    g = L.GemmDesc()
+    g.n_a = 0
+    assert "n_a=0 out of range" in err(lib.omg_gemm(C.byref(g), None))
+    g.n_a, g.n_segs = 1, 99
+    assert "n_segs=99 out of range" in err(lib.omg_gemm(C.byref(g), None))
+    f = L.FuseDesc()
+    f.n_concepts, f.noise_main, f.latents = 9, 0x1000, 0x1000
+    assert "n_concepts=9 out of range" in err(lib.omg_fuse_step(C.byref(f), None))
+    assert "bad channel split" in err(lib.omg_groupnorm(fake, 100, None, 0, 1, 16, fake, fake, 1e-5, 0, fake, fake, None))
