@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """OMG + LoRA multi-concept generation on the B200 path.  Same flags, prompt mini-DSL, two-stage flow and output
 files as the reference CLI (inference_lora.py:201-323); additions (non-breaking): --synthetic, --num_inference_steps,
---image_size, --mask_boxes.
+--image_size, --mask_boxes, --vae_fp16_safe.
 
 The segmentation models between the stages (YOLO-World / GroundingDINO + SAM) and the VAE / text encoders are outside
 the accelerated hot path: masks come from --mask_boxes (x0,y0,x1,y1 per concept, '|' separated) or,
@@ -72,6 +72,8 @@ def parse_args():
     p.add_argument("--tiny", action="store_true", help="with --synthetic: toy widths (plumbing check)")
     p.add_argument("--decode", action="store_true", help="with --synthetic: decode with a random-init VAE decoder")
     p.add_argument("--mask_boxes", default="", type=str, help="x0,y0,x1,y1|x0,y0,x1,y1 (pixels), replaces segmentation")
+    p.add_argument("--vae_fp16_safe", default="", type=str, help="directory of fp16-safe SDXL VAE weights: decode to "
+                   "PNG on the GPU (without it the latents are saved)")
     return p.parse_args()
 
 
@@ -105,15 +107,19 @@ def build_model_sd(args, prompts, device):
     cfg = UNetConfig.sdxl()
     unet = PackedUNet(cfg, ck.load_unet_weights(args.pretrained_sdxl_model, "unet"), device=device)
     controlnet = None
-    if args.spatial_condition and os.path.isdir(args.controlnet_checkpoint):
+    if args.spatial_condition and os.path.exists(args.spatial_condition):
         controlnet = PackedUNet(cfg, ck.load_unet_weights(args.controlnet_checkpoint, "", None), device=device,
                                 controlnet=True)
     enc = ClipPromptEncoder.from_pretrained(args.pretrained_sdxl_model, device)
     vae = None
-    if os.path.isdir(os.path.join(args.pretrained_sdxl_model, "vae")):
+    if args.vae_fp16_safe:
+        # opt-in: the decoder runs fp16 activations, which the ORIGINAL SDXL VAE weights overflow (the reference
+        # up-casts the VAE to fp32, lora_pipeline.py:635-646); point this at the fp16-safe re-export (same keys).
+        # The decoder raises on non-finite output instead of writing black PNGs.  Default output: latents.
         from omg_b200.vae import PackedVaeDecoder
-        # fp16 activations: needs the fp16-safe re-export of the SDXL VAE weights (same keys); see omg_b200/vae.py
-        vae = PackedVaeDecoder(ck.load_unet_weights(args.pretrained_sdxl_model, "vae"), device=device)
+        vae_dir = args.vae_fp16_safe
+        sub = "vae" if os.path.isdir(os.path.join(vae_dir, "vae")) else ""
+        vae = PackedVaeDecoder(ck.load_unet_weights(vae_dir, sub, None), device=device)
     pipe = LoraMultiConceptPipeline(unet, controlnet=controlnet, prompt_encoder=enc, vae_decoder=vae)
     controller = AttentionReplace(prompts, 50, cross_replace_steps={"default_": 1.}, self_replace_steps=0.4,
                                   tokenizer=enc.tokenizer, width=args.image_size // 32, height=args.image_size // 32)
@@ -139,7 +145,18 @@ if __name__ == "__main__":
     device = torch.device("cuda")
     prompts = [args.prompt] * 2
     width = height = args.image_size
-    kwargs = {"height": height, "width": width, "spatial_condition": None, "output_type": "latent"}
+    # pose condition (inference_lora.py:241-246): opened, RGB, resized to the image size, passed as `image=`
+    spatial_condition = None
+    if args.spatial_condition:
+        if os.path.exists(args.spatial_condition):
+            from PIL import Image
+            spatial_condition = Image.open(args.spatial_condition).convert("RGB").resize((width, height))
+            print("use pose condition")
+        else:
+            raise SystemExit(f"--spatial_condition {args.spatial_condition}: no such file")
+        if args.synthetic:
+            raise SystemExit("--spatial_condition needs the real ControlNet checkpoint (not available with --synthetic)")
+    kwargs = {"height": height, "width": width, "spatial_condition": spatial_condition, "output_type": "latent"}
     build = build_model_synthetic if args.synthetic else build_model_sd
     pipe, controller, pipe_concepts, pipe_list, synth_masks = build(args, prompts, device)
     pipe.dedup = args.dedup

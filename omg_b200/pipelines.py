@@ -61,6 +61,19 @@ class ConceptModels:
         self._active: Tuple[Tuple[str, ...], Tuple[float, ...]] = ((), ())
         self.image_proj = None  # (state dict, heads, dim_head) of the Resampler
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model, unet: Optional[PackedUNet] = None, prompt_encoder=None,
+                        torch_dtype=torch.float16, variant: Optional[str] = "fp16", device="cuda", **_):
+        """`StableDiffusionXLPipeline.from_pretrained(pretrained_model, torch_dtype=float16, variant="fp16")` /
+        `InstantidSingleConceptPipeline.from_pretrained(...)` as the reference builds its concept pipeline
+        (inference_lora.py:159, inference_instantid.py:206-210).  `unet=` shares already packed base weights (the
+        reference loads the same checkpoint twice; the packed weights are immutable, so one copy serves both)."""
+        unet, prompt_encoder = _load_base(pretrained_model, unet, prompt_encoder, torch_dtype, variant, device)
+        return cls(unet, prompt_encoder=prompt_encoder)
+
+    def to(self, device=None, *_, **__):
+        return self
+
     @property
     def _execution_device(self):
         return self.unet.device
@@ -91,7 +104,10 @@ class ConceptModels:
         if getattr(self.prompt_encoder, "supports_adapters", False):  # text-encoder LoRA of the active adapters
             kw["adapters"] = (*self._active, getattr(self, "text_encoder_loras", {}))
         pe, pp = self.prompt_encoder(prompt, lora_scale, **kw)
-        ne, np_ = self.prompt_encoder(negative_prompt or "", lora_scale, **kw)
+        if negative_prompt is None:  # SDXL force_zeros_for_empty_prompt [3P encode_prompt]: zeros, not encode("")
+            ne, np_ = torch.zeros_like(pe), torch.zeros_like(pp)
+        else:
+            ne, np_ = self.prompt_encoder(negative_prompt, lora_scale, **kw)
         return pe[None], ne[None], pp[None], np_[None]
 
     # --- InstantID pieces (instantid_single_pieline.py:159-243) --------------------------------------------
@@ -116,6 +132,25 @@ class ConceptModels:
             emb = torch.cat([torch.zeros_like(emb), emb], dim=0)
         sd, heads, dim_head = self.image_proj
         return resampler_forward(sd, emb.to(next(iter(sd.values())).device), heads, dim_head)
+
+
+def _load_base(pretrained_model, unet, prompt_encoder, torch_dtype, variant, device):
+    """UNet weights (`<dir>/unet/diffusion_pytorch_model[.fp16].safetensors`) and the two CLIP towers of an SDXL
+    diffusers checkout."""
+    from . import checkpoints as ck
+    if unet is None:
+        unet = PackedUNet(UNetConfig.sdxl(), ck.load_unet_weights(os.fspath(pretrained_model), "unet", variant), device=device)
+    if prompt_encoder is None:
+        from .text import ClipPromptEncoder
+        prompt_encoder = ClipPromptEncoder.from_pretrained(os.fspath(pretrained_model), device, torch_dtype)
+    return unet, prompt_encoder
+
+
+def load_controlnet(path, device="cuda", variant: Optional[str] = None) -> PackedUNet:
+    """`ControlNetModel.from_pretrained(path, torch_dtype=float16)` (inference_lora.py:153,
+    inference_instantid.py:196,205,219): a directory holding diffusion_pytorch_model[.fp16].safetensors."""
+    from . import checkpoints as ck
+    return PackedUNet(UNetConfig.sdxl(), ck.load_unet_weights(os.fspath(path), "", variant), device=device, controlnet=True)
 
 
 def _resolve_lora(owner, lora, adapter_name: str, weight_name: Optional[str]):
@@ -163,6 +198,31 @@ class _BasePipeline:
         self._prefix: Optional[dict] = None
         self.sample_forwards = 0  # UNet sample-forwards executed by the last call (296 per image as-executed)
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model, controlnet=None, torch_dtype=torch.float16, variant: Optional[str] = "fp16",
+                        device="cuda", unet: Optional[PackedUNet] = None, prompt_encoder=None, vae_decoder=None,
+                        use_graphs: bool = True, **_):
+        """`LoraMultiConceptPipeline.from_pretrained(pretrained_model, controlnet=controlnet, torch_dtype=float16,
+        variant="fp16")` (inference_lora.py:154-155, inference_instantid.py:197-198).  controlnet: a PackedUNet, a
+        checkpoint directory, or None.  The VAE is not loaded here: fp16 activations need the fp16-safe VAE weights,
+        so image output is opt-in through `vae_decoder=` (default output is latents)."""
+        unet, prompt_encoder = _load_base(pretrained_model, unet, prompt_encoder, torch_dtype, variant, device)
+        if isinstance(controlnet, (str, os.PathLike)):
+            controlnet = load_controlnet(controlnet, device)
+        pipe = cls(unet, controlnet=controlnet, prompt_encoder=prompt_encoder, vae_decoder=vae_decoder, use_graphs=use_graphs)
+        return pipe
+
+    def to(self, device=None, *_, **__):
+        return self
+
+    @property
+    def tokenizer(self):
+        """`pipe.tokenizer` as the CLIs use it (inference_lora.py:156,277): the first CLIP tokenizer."""
+        tok = getattr(self.prompt_encoder, "tokenizer", None)
+        if tok is None:
+            raise AttributeError("this pipeline's prompt encoder has no tokenizer (synthetic encoder)")
+        return tok
+
     @property
     def _execution_device(self):
         return self.unet.device
@@ -196,7 +256,10 @@ class _BasePipeline:
             kw["adapters"] = (names, tuple(1.0 for _ in names), self.text_encoder_loras)
         for p, n in zip(prompts, negs):
             e, pooled = self.prompt_encoder(p, lora_scale, **kw)
-            e2, pooled2 = self.prompt_encoder(n or "", lora_scale, **kw)
+            if n is None:  # force_zeros_for_empty_prompt [3P]: a missing negative prompt is zeros, not encode("")
+                e2, pooled2 = torch.zeros_like(e), torch.zeros_like(pooled)
+            else:
+                e2, pooled2 = self.prompt_encoder(n, lora_scale, **kw)
             pe.append(e), pp.append(pooled), ne.append(e2), np_.append(pooled2)
         return torch.stack(pe), torch.stack(ne), torch.stack(pp), torch.stack(np_)
 
@@ -384,23 +447,24 @@ class _BasePipeline:
                         for r in (4 + 2 * j, 5 + 2 * j):
                             variant["ip_items"].append((r, r, n_ip, n_ip))
                             n_ip += 1
+            slots = []
             if cn is not None:
                 cn.sample_in.copy_(main.sample_in)
                 down, mid = cn.forward(i, key=("cn",))
                 sc = cn_scale * cn_keep(i)
-                run.residuals_in = (down, mid, sc, 0)
+                slots.append((down, mid, sc, 0))
                 key = key + (sc,)
             if fuse and idr is not None:
                 for j in range(n_act):
                     idr.sample_in[2 * j:2 * j + 2].copy_(cbuf)
-                down, mid = idr.forward(i, key=("identity",))
+                id_down, id_mid = idr.forward(i, key=("identity",))
             if run is fused and idr is not None:
-                # IdentityNet residuals go to the concept rows only; a main-row ControlNet would need a second slot
-                if cn is not None:
-                    raise NotImplementedError("main-pass ControlNet together with IdentityNet in one grouped forward")
-                run.residuals_in = (down, mid, id_scale, 4)
+                # IdentityNet residuals go to the concept rows (4 ..), a main-pass ControlNet's to rows 0-3: two
+                # residual slots of the same grouped forward
+                slots.append((id_down, id_mid, id_scale, 4))
                 variant["residuals"] = True
                 key = key + ("id", id_scale)
+            run.residuals_in = slots
             noise = run.forward(i, variant, key=key)
             if controller is not None:
                 controller.advance(n_att)
@@ -414,7 +478,7 @@ class _BasePipeline:
                         v = r.default_variant()
                         ckey = ("concept",)
                         if idr is not None:
-                            r.residuals_in = ([d[2 * j:2 * j + 2] for d in down], mid[2 * j:2 * j + 2], id_scale, 0)
+                            r.residuals_in = ([d[2 * j:2 * j + 2] for d in id_down], id_mid[2 * j:2 * j + 2], id_scale, 0)
                             v["residuals"] = True
                             ckey = ("concept", "id", id_scale)
                         noises.append(r.forward(i, v, key=ckey))

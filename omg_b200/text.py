@@ -62,6 +62,9 @@ class ClipPromptEncoder:
             for n, w in zip(names, weights):
                 for full, (A, B, s) in (store.get(n) or {}).items():
                     te, _, flat = full.partition(".")
+                    # kohya files flatten the module path with '_', diffusers / peft files keep the dots
+                    # (`text_encoder.text_model.encoder.layers.0.self_attn.q_proj.lora_A.weight`): one spelling here
+                    flat = flat.replace(".", "_")
                     idx = {"te1": 0, "te2": 1}.get(te)
                     if idx is None or idx >= len(self._flat):
                         continue

@@ -154,6 +154,9 @@ class PackedUNet:
         self.lora_sets: Dict[str, Dict[str, Tuple[torch.Tensor, torch.Tensor]]] = {}
         self.ip: Optional[Dict[str, torch.Tensor]] = None
         self.ip_scale, self.ip_tokens = 1.0, 16
+        # bumped whenever something a captured CUDA graph may have baked in changes (LoRA sets, IP-adapter weights,
+        # the IP scale scalar): runners drop their graphs when they see a new version
+        self.adapter_version = 0
 
     # ------------------------------------------------------------------------------------------- adapters
     def add_lora_set(self, key: str, adapters, global_scale: float = 1.0):
@@ -228,15 +231,19 @@ class PackedUNet:
         if unsupported:
             raise ValueError(f"LoRA targets outside the transformer Linears are not supported: {sorted(unsupported)[:4]}…")
         self.lora_sets[key] = packed
+        self.adapter_version += 1
 
     def set_ip_adapter(self, ip_weights: Dict[str, Tuple[torch.Tensor, torch.Tensor]], scale: float = 1.0,
                        num_tokens: int = 16):
         """IPAttnProcessor weights (src/ip_adapter/attention_processor.py:107-108): attn2 path -> (to_k_ip, to_v_ip)."""
         self.ip = {k: _f16(torch.cat([wk, wv], dim=0), self.device) for k, (wk, wv) in ip_weights.items()}
         self.ip_scale, self.ip_tokens = float(scale), int(num_tokens)
+        self.adapter_version += 1
 
     def set_ip_adapter_scale(self, scale: float):
-        self.ip_scale = float(scale)
+        if float(scale) != self.ip_scale:
+            self.ip_scale = float(scale)
+            self.adapter_version += 1
 
     def num_attention_layers(self) -> int:
         return 2 * sum(layers for _, _, layers in self.tr_names)
@@ -272,6 +279,8 @@ class UNetRunner:
         self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.graph_launches: Dict[tuple, int] = {}
         self.warm: set = set()
+        self._out: Dict[tuple, object] = {}
+        self._graph_version = model.adapter_version
         self.temb_table = None
         self.kv: Dict[str, torch.Tensor] = {}
         self.kv_ip: Dict[str, torch.Tensor] = {}
@@ -282,32 +291,38 @@ class UNetRunner:
         self.cross_items: List[List[tuple]] = []
         self.cross_weights: List[float] = []
         self.cond_emb = None
-        # (9 skip residual tensors, mid residual, scale[, row0]) produced by a ControlNet runner; added to the batch
-        # rows [row0, row0 + residual batch)
+        # one slot, or a list of slots, (9 skip residual tensors, mid residual, scale[, row0]) produced by ControlNet
+        # runners; a slot is added to the batch rows [row0, row0 + residual batch)
         self.residuals_in = None
         self.stats_ws = torch.empty(batch * 64 * 257, dtype=torch.float32, device=self.dev)
 
     # ------------------------------------------------------------------------------------------- buffers
-    def buf(self, name, shape) -> torch.Tensor:
+    def drop_graphs(self):
+        """Forget every captured graph (they hold raw device pointers and launch-time scalars)."""
+        self.graphs.clear()
+        self.graph_launches.clear()
+        self.warm.clear()
+        self._out.clear()
+
+    def _alloc(self, name, shape, dtype, zero) -> torch.Tensor:
         t = self.ws.get(name)
         if t is None or tuple(t.shape) != tuple(shape):
-            t = torch.empty(shape, dtype=torch.float16, device=self.dev)
+            if t is not None and self.graphs:
+                # a buffer a captured graph may point at is being replaced (e.g. the K/V rows change when a
+                # controller is added to / removed from the same runner): the old graphs are stale
+                self.drop_graphs()
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.dev)
             self.ws[name] = t
         return t
+
+    def buf(self, name, shape) -> torch.Tensor:
+        return self._alloc(name, shape, torch.float16, False)
 
     def zbuf(self, name, shape) -> torch.Tensor:
-        t = self.ws.get(name)
-        if t is None or tuple(t.shape) != tuple(shape):
-            t = torch.zeros(shape, dtype=torch.float16, device=self.dev)
-            self.ws[name] = t
-        return t
+        return self._alloc(name, shape, torch.float16, True)
 
     def fbuf(self, name, shape) -> torch.Tensor:
-        t = self.ws.get(name)
-        if t is None or tuple(t.shape) != tuple(shape):
-            t = torch.zeros(shape, dtype=torch.float32, device=self.dev)
-            self.ws[name] = t
-        return t
+        return self._alloc(name, shape, torch.float32, True)
 
     def _ln_vectors(self, key, groups, n, active):
         """c1 / c2 planes of the folded LayerNorm for every row group: the LoRA delta  s B (A' x)  is linear in the
@@ -502,7 +517,11 @@ class UNetRunner:
         for i in range(2 * (len(cfg.cond_embed_channels) - 1)):
             f = ops.conv3x3_s2 if i % 2 == 1 else ops.conv3x3
             h = self._silu(f(h, P[f"cond.{i}.w"], bias=P[f"cond.{i}.b"]))
-        self.cond_emb = ops.conv3x3(h, P["cond.conv_out.w"], bias=P["cond.conv_out.b"])
+        # persistent buffer: the captured ControlNet graph reads it through a raw pointer (conv_in's residual), so a
+        # new condition image must land in the SAME memory
+        Bc, Hc, Wc, _ = h.shape
+        self.cond_emb = ops.conv3x3(h, P["cond.conv_out.w"], bias=P["cond.conv_out.b"],
+                                    out=self.buf("cond_emb", (Bc, Hc, Wc, P["cond.conv_out.b"].shape[0])))
 
     @staticmethod
     def _silu(t):
@@ -611,12 +630,16 @@ class UNetRunner:
                         out=self.buf("conv_in.out", (B, H, W, cfg.block_out_channels[0])))
         h, skips = self._encoder(h, variant)
         if variant.get("residuals", False):
-            # ControlNet outputs * conditioning_scale, added in place to the rows of the stream they belong to
-            down_r, mid_r, r_scale = self.residuals_in[:3]
-            r0 = self.residuals_in[3] if len(self.residuals_in) > 3 else 0
-            for sk, r in zip(skips + [h], list(down_r) + [mid_r]):
-                dst = sk[r0:r0 + r.shape[0]]
-                ops.axpy(dst, r, r_scale, out=dst)
+            # ControlNet outputs * conditioning_scale, added in place to the rows of the stream they belong to.  Several
+            # slots may be active in one grouped forward: the main-pass ControlNet on rows 0-3 and the IdentityNet on
+            # the concept rows (instantid_pipeline.py:574-616 and :639-674 run in the same step).
+            slots = self.residuals_in if isinstance(self.residuals_in, list) else [self.residuals_in]
+            for slot in slots:
+                down_r, mid_r, r_scale = slot[:3]
+                r0 = slot[3] if len(slot) > 3 else 0
+                for sk, r in zip(skips + [h], list(down_r) + [mid_r]):
+                    dst = sk[r0:r0 + r.shape[0]]
+                    ops.axpy(dst, r, r_scale, out=dst)
         nb = len(cfg.block_out_channels)
         for i in range(nb):
             ch, layers = cfg.block_out_channels[nb - 1 - i], cfg.transformer_layers[nb - 1 - i]
@@ -673,13 +696,15 @@ class UNetRunner:
         fn = self._forward_controlnet if self.m.controlnet else self._forward_unet
         if not self.use_graphs or key is None:
             return fn(variant)
+        if self._graph_version != self.m.adapter_version:  # adapters / IP scale changed since the graphs were captured
+            self.drop_graphs()
+            self._graph_version = self.m.adapter_version
         if key in self.graphs:
             self.graphs[key].replay()
             REPLAYED_LAUNCHES[0] += self.graph_launches[key]
             return self._out[key]
         if key not in self.warm:
             self.warm.add(key)
-            self._out = getattr(self, "_out", {})
             self._out[key] = fn(variant)  # eager run: allocates buffers, sets kernel attributes
             return self._out[key]
         g = torch.cuda.CUDAGraph()

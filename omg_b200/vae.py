@@ -225,7 +225,13 @@ class PackedVaeDecoder:
     def __call__(self, latents: torch.Tensor, output_type: str = "pt"):
         """The pipelines' `vae_decoder(latents, output_type)`: VaeImageProcessor.postprocess [3P] - denormalise to
         [0, 1]; 'pt' tensor (B,3,H,W), 'np' array (B,H,W,3), 'pil' list of images."""
-        img = (self.decode(latents).float() / 2 + 0.5).clamp(0, 1)
+        dec = self.decode(latents).float()
+        if not bool(torch.isfinite(dec).all()):
+            # fp16 activations overflow with the original SDXL VAE weights (the reference up-casts this module to
+            # fp32 for that reason, lora_pipeline.py:635-646): refuse to hand back NaN / black images
+            raise FloatingPointError("VAE decode produced non-finite values in fp16: use the fp16-safe SDXL VAE "
+                                     "weights (same keys) or output_type='latent'")
+        img = (dec / 2 + 0.5).clamp(0, 1)
         if output_type == "pt":
             return img
         arr = img.permute(0, 2, 3, 1).cpu().numpy()

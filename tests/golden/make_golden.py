@@ -170,7 +170,7 @@ def make_kps():
     np.savez_compressed(os.path.join(OUT, "kps.npz"), kps=np.array(kps), image=img)
 
 
-def _extract(path, name, cls=None):
+def _extract(path, name, cls=None, extra_globals=None):
     import ast
     tree = ast.parse(open(os.path.join(REF, path)).read())
     body = tree.body
@@ -178,6 +178,7 @@ def _extract(path, name, cls=None):
         body = next(n for n in body if isinstance(n, ast.ClassDef) and n.name == cls).body
     fn = next(n for n in body if isinstance(n, ast.FunctionDef) and n.name == name)
     ns = {"torch": torch, "F": torch.nn.functional}
+    ns.update(extra_globals or {})
     exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
     return ns[name]
 
@@ -368,7 +369,26 @@ def make_cli():
     torch.save(out, os.path.join(OUT, "cli.pt"))
 
 
+def make_cli_flags():
+    """Flag names, defaults and types of both CLIs' parse_args (inference_lora.py:203-222,
+    inference_instantid.py:259-286): the function is cut out of the file by ast and run against argparse."""
+    import argparse
+    import json
+    out = {}
+    for fname in ("inference_lora.py", "inference_instantid.py"):
+        fn = _extract(fname, "parse_args", extra_globals={"argparse": argparse})
+        argv, sys.argv = sys.argv, ["x"]
+        try:
+            ns = fn()
+        finally:
+            sys.argv = argv
+        out[fname] = {k: [v, type(v).__name__] for k, v in sorted(vars(ns).items())}
+    with open(os.path.join(OUT, "cli_flags.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
+    make_cli_flags()
     make_fusion_instantid()
     make_region_attn()
     make_fusion()

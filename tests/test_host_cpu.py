@@ -210,3 +210,26 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
     f.n_concepts, f.noise_main, f.latents = 9, 0x1000, 0x1000
     assert "n_concepts=9 out of range" in err(lib.omg_fuse_step(C.byref(f), None))
     assert "bad channel split" in err(lib.omg_groupnorm(fake, 100, None, 0, 1, 16, fake, fake, 1e-5, 0, fake, fake, None))
+
+
+def test_cli_flags_match_the_reference_parse_args():
+    """Every flag of the reference CLIs (inference_lora.py:203-222, inference_instantid.py:259-286; names, defaults and
+    types extracted from the reference files by tests/golden/make_golden.py) exists here with the same default;
+    extra flags are additive."""
+    import importlib.util
+    import json
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = json.load(open(os.path.join(root, "tests", "golden", "cli_flags.json")))
+    for fname, flags in gold.items():
+        spec = importlib.util.spec_from_file_location("cli_" + fname[:-3], os.path.join(root, fname))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        argv, sys.argv = sys.argv, [fname]
+        try:
+            ns = vars(mod.parse_args())
+        finally:
+            sys.argv = argv
+        for name, (default, tname) in flags.items():
+            assert name in ns, f"{fname}: flag --{name} of the reference is missing"
+            assert ns[name] == default and type(ns[name]).__name__ == tname, (fname, name, ns[name], default)

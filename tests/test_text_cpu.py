@@ -74,3 +74,28 @@ def test_concept_models_pass_active_adapters():
     cm.set_adapters(["a", "style"], adapter_weights=[0.7, 0.5])
     cm.encode_prompt("p", "n", lora_scale=0.8)
     assert seen["adapters"][0] == ("a", "style") and seen["adapters"][1] == (0.7, 0.5)
+
+
+def test_peft_layout_text_encoder_lora_merges():
+    """diffusers / peft files spell the module path with dots (`text_encoder.text_model.encoder.layers.0.self_attn.
+    q_proj.lora_A.weight`); omg_b200.checkpoints returns them as `te1.text_model.encoder...` and the merge must find
+    the same Linear as for the kohya spelling."""
+    from omg_b200.checkpoints import convert_lora_state_dict
+    from omg_b200.text import ClipPromptEncoder
+    e1, e2 = _towers()
+    enc = ClipPromptEncoder([ToyTokenizer(), ToyTokenizer()], [e1, e2], device="cpu", dtype=torch.float32)
+    g = torch.Generator().manual_seed(2)
+    A1, B1 = torch.randn(2, 32, generator=g) * 0.3, torch.randn(32, 2, generator=g) * 0.3
+    A2, B2 = torch.randn(2, 48, generator=g) * 0.3, torch.randn(48, 2, generator=g) * 0.3
+    sd = {"text_encoder.text_model.encoder.layers.0.self_attn.q_proj.lora_A.weight": A1,
+          "text_encoder.text_model.encoder.layers.0.self_attn.q_proj.lora_B.weight": B1,
+          "text_encoder_2.text_model.encoder.layers.1.self_attn.v_proj.lora_A.weight": A2,
+          "text_encoder_2.text_model.encoder.layers.1.self_attn.v_proj.lora_B.weight": B2}
+    _unet, te, _skipped = convert_lora_state_dict(sd)
+    assert set(te) == {"te1.text_model.encoder.layers.0.self_attn.q_proj", "te2.text_model.encoder.layers.1.self_attn.v_proj"}
+    w1 = e1.text_model.encoder.layers[0].self_attn.q_proj.weight.detach().clone()
+    w2 = e2.text_model.encoder.layers[1].self_attn.v_proj.weight.detach().clone()
+    enc("a b", 0.8, adapters=(("style",), (1.0,), {"style": te}))
+    s1, s2 = te["te1.text_model.encoder.layers.0.self_attn.q_proj"][2], te["te2.text_model.encoder.layers.1.self_attn.v_proj"][2]
+    assert torch.allclose(e1.text_model.encoder.layers[0].self_attn.q_proj.weight.detach(), w1 + (B1 @ A1) * (s1 * 0.8), atol=1e-6)
+    assert torch.allclose(e2.text_model.encoder.layers[1].self_attn.v_proj.weight.detach(), w2 + (B2 @ A2) * (s2 * 0.8), atol=1e-6)
