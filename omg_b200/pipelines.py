@@ -316,8 +316,22 @@ class _BasePipeline:
             for r in runners:
                 r.update_context_rows(4, rows)
 
+    def _step_end(self, callback, i, t, lat, main, cbuf):
+        """`callback_on_step_end(self, i, t, {"latents": latents})` (lora_pipeline.py:617-625): the callback sees the
+        latents after the scheduler step as (2,4,h,w) and may return {"latents": replacement}."""
+        view = lat.permute(0, 3, 1, 2)
+        given = view.clone()
+        out = callback(self, i, t, {"latents": given})
+        new = (out or {}).get("latents", given)
+        if new is not given:
+            lat.copy_(new.to(lat.device, lat.dtype).permute(0, 2, 3, 1))
+            if i + 1 < len(self.scheduler.sigmas) - 1:  # next step's scaled inputs (fuse_step wrote them from the old latents)
+                x = (lat * self.scheduler.input_scale(i + 1)).half()
+                main.sample_in[..., :4] = torch.cat([x, x], dim=0)
+                cbuf[..., :4] = torch.cat([x[1:2], x[1:2]], dim=0)
+
     def _denoise(self, *, ts, lat, ctx4, pooled4, tid, concepts, masks, stage, guidance_scale, h, w, concept_unet,
-                 main_cn=None, identity=None):
+                 main_cn=None, identity=None, callback=None):
         """The step loop (lora_pipeline.py:485-632 / instantid_pipeline.py:540-690).
 
         concepts: list of dicts {ctx (2, L, D) [text tokens (+ IP tokens)], pooled (2, P), lora_key, ip (bool)};
@@ -422,6 +436,8 @@ class _BasePipeline:
                     controller.advance(n_att)
                 self.sample_forwards += 2
                 ops.fuse_step(noise4, [], [], guidance_scale, float(sig[i]), float(sig[i + 1]), lat, main.sample_in, cbuf)
+                if callback is not None:
+                    self._step_end(callback, i, ts[i], lat, main, cbuf)
                 if lat0_keep is not None and i == FUSION_AFTER_STEP:
                     self._prefix = {"key": sig_key, "lat0": lat0_keep, "ctx4": ctx4.to(dev).clone(),
                                     "pooled4": pooled4.to(dev).clone(), "lat": lat.clone(),
@@ -486,6 +502,8 @@ class _BasePipeline:
             self.sample_forwards += 4 + (2 * n_act if fuse else 0)
             ops.fuse_step(noise[0:4] if run is fused else noise, noises, fmasks, guidance_scale, float(sig[i]),
                           float(sig[i + 1]), lat, main.sample_in, cbuf)
+            if callback is not None:
+                self._step_end(callback, i, ts[i], lat, main, cbuf)
             if lat0_keep is not None and i == FUSION_AFTER_STEP:
                 self._prefix = {"key": sig_key, "lat0": lat0_keep, "ctx4": ctx4.to(dev).clone(),
                                 "pooled4": pooled4.to(dev).clone(), "lat": lat.clone(),
@@ -515,7 +533,8 @@ class LoraMultiConceptPipeline(_BasePipeline):
                  return_dict: bool = True, cross_attention_kwargs=None, controlnet_conditioning_scale=1.0,
                  guess_mode: bool = False, control_guidance_start=0.0, control_guidance_end=1.0, original_size=None,
                  crops_coords_top_left=(0, 0), target_size=None, controller=None, concept_models: ConceptModels = None,
-                 stage=None, region_masks=None, lora_list=None, styleL=None, region_prompt_embeds=None, **kwargs):
+                 stage=None, region_masks=None, lora_list=None, styleL=None, region_prompt_embeds=None,
+                 callback_on_step_end=None, **kwargs):
         dev = self._execution_device
         scale = (cross_attention_kwargs or {}).get("scale", 1.0)
         # 3.1 prompts: prompt = [[global, global], [(region, region_neg), ...]]  (lora_pipeline.py:310-347)
@@ -568,7 +587,7 @@ class LoraMultiConceptPipeline(_BasePipeline):
             c["ip"] = False
         lat = self._denoise(ts=ts, lat=lat, ctx4=ctx4, pooled4=pooled4, tid=tid, concepts=concepts, masks=masks,
                             stage=stage, guidance_scale=guidance_scale, h=h, w=w, concept_unet=concept_models.unet
-                            if concept_models is not None else self.unet, main_cn=main_cn)
+                            if concept_models is not None else self.unet, main_cn=main_cn, callback=callback_on_step_end)
         return self._finish(lat, output_type, return_dict)
 
     def _prepare_image(self, image, width, height, batch):
@@ -608,7 +627,7 @@ class InstantidMultiConceptPipeline(_BasePipeline):
                  controller=None, concept_models: ConceptModels = None, stage=None, region_masks=None, face_app=None,
                  t2i_image=None, t2i_controlnet_conditioning_scale=1.0, face_embeds=None, prompt_embeds=None,
                  negative_prompt_embeds=None, pooled_prompt_embeds=None, negative_pooled_prompt_embeds=None,
-                 region_prompt_embeds=None, **kwargs):
+                 region_prompt_embeds=None, callback_on_step_end=None, **kwargs):
         dev = self._execution_device
         scale = (cross_attention_kwargs or {}).get("scale", 1.0)
         global_prompt = prompt[0]
@@ -661,7 +680,8 @@ class InstantidMultiConceptPipeline(_BasePipeline):
                         [c["tokens"] for c in concepts])
         lat = self._denoise(ts=ts, lat=lat, ctx4=ctx4, pooled4=pooled4, tid=tid, concepts=concepts, masks=masks,
                             stage=stage, guidance_scale=guidance_scale, h=h, w=w, concept_unet=concept_models.unet
-                            if concept_models is not None else self.unet, main_cn=main_cn, identity=identity)
+                            if concept_models is not None else self.unet, main_cn=main_cn, identity=identity,
+                            callback=callback_on_step_end)
         return self._finish(lat, output_type, return_dict)
 
     def get_face_embedding(self, face_app, ref_image):

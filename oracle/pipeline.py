@@ -28,7 +28,8 @@ class Concept:
 
 def get_region_mask(mask_list, fh, fw):
     """lora_pipeline.py:674-681."""
-    exclusive = torch.zeros((fh, fw))
+    dev = next((m.device for m in mask_list if m is not None), "cpu")  # the reference builds it on the CPU (:675)
+    exclusive = torch.zeros((fh, fw), device=dev)
     for mask in mask_list:
         if mask is not None:
             m = F.interpolate(mask[None, None].float(), size=(fh, fw), mode="nearest").squeeze().to(exclusive.dtype)
@@ -39,6 +40,7 @@ def get_region_mask(mask_list, fh, fw):
 def fuse_noise(noise_pred, region_noises, mask_list):
     """lora_pipeline.py:569-607 with replace_ratio = 1."""
     fh, fw = noise_pred.shape[2], noise_pred.shape[3]
+    mask_list = [None if m is None else m.to(noise_pred.device) for m in mask_list]
     region_mask = get_region_mask(mask_list, fh, fw)
     edit = torch.cat([noise_pred[1:2], noise_pred[3:4]], dim=0)
     new = torch.zeros_like(edit)

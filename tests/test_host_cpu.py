@@ -233,3 +233,41 @@ def test_cli_flags_match_the_reference_parse_args():
         for name, (default, tname) in flags.items():
             assert name in ns, f"{fname}: flag --{name} of the reference is missing"
             assert ns[name] == default and type(ns[name]).__name__ == tname, (fname, name, ns[name], default)
+
+
+def test_product_resampler_matches_reference_golden():
+    """omg_b200.resampler.resampler_forward (the function ConceptModels._encode_prompt_image_emb runs)
+    against the output of the reference's own Resampler module (tests/golden/resampler.pt, src/ip_adapter/
+    resampler.py:109-120)."""
+    import os
+    from omg_b200.resampler import resampler_forward
+    d = torch.load(os.path.join(os.path.dirname(__file__), "golden", "resampler.pt"))
+    y = resampler_forward(d["sd"], d["x"], d["heads"], d["dim_head"])
+    assert y.shape == d["y"].shape and torch.allclose(y, d["y"], atol=2e-6)
+
+
+def test_latent_init_follows_the_reference_generator_call():
+    """A15 (lora_pipeline.py:397-409): latents = randn((1,4,h,w), generator, fp16) * init_noise_sigma, duplicated.  The
+    product's prepare_latents must draw the SAME numbers from the same seeded generator (one randn call of that shape
+    and dtype) - checked here on the host generator the CLIs use when CUDA is absent, and on cuda in the GPU test."""
+    from omg_b200.pipelines import _BasePipeline
+    from omg_b200.scheduler import EulerDiscreteSchedule
+
+    class P(_BasePipeline):
+        def __init__(self):
+            self.scheduler = EulerDiscreteSchedule()
+            self.scheduler.set_timesteps(30)
+
+        _execution_device = torch.device("cpu")
+
+    pipe = P()
+    g = torch.Generator().manual_seed(14)
+    lat = pipe.prepare_latents(16, 24, g, None)
+    ref = torch.randn((1, 4, 16, 24), generator=torch.Generator().manual_seed(14), dtype=torch.float16)
+    ref = ref.float() * pipe.scheduler.init_noise_sigma
+    assert lat.shape == (2, 16, 24, 4) and lat.dtype == torch.float32
+    assert torch.equal(lat[0], ref[0].permute(1, 2, 0)) and torch.equal(lat[1], lat[0])
+    # the generator state advanced by exactly that one call
+    assert torch.equal(torch.randn(3, generator=g),
+                       (lambda h: (torch.randn((1, 4, 16, 24), generator=h, dtype=torch.float16), torch.randn(3, generator=h))[1])(
+                           torch.Generator().manual_seed(14)))

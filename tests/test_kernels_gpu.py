@@ -347,9 +347,6 @@ def test_tall_tiles_conv_rowvec_and_stats(ops):
     assert torch.allclose(s[:, 1], (href * href).sum(1), rtol=3e-3, atol=2e-2)
 
 
-@pytest.mark.xfail(strict=False, reason="written after round 1's GPU minutes were spent: not yet executed on a B200 "
-                   "(the oracle side of the same golden is checked on CPU in test_oracle_golden.py); drop the mark "
-                   "once it has run")
 def test_fuse_step_matches_the_reference_fusion_statements(ops):
     """omg_fuse_step against tests/golden/fusion.pt: the output of the reference's own fusion + guidance statements
     (lora_pipeline.py:568-612, executed from the method's AST): one concept without a mask (skipped), two overlapping

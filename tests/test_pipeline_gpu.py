@@ -210,3 +210,46 @@ def test_dedup_mode_reproduces_the_as_executed_result():
     pipe(stage=2, latents=lat1, region_masks=wl.masks, **kw)
     assert pipe.sample_forwards == 2 * 16 + 2 * 8
     ctrl.reset()
+
+
+def test_generator_only_latent_path_matches_the_reference_call():
+    """A15: with `generator=` and no `latents=` the pipeline draws randn((1,4,h,w), generator, fp16) on the generator's
+    device exactly like prepare_latents / randn_tensor (lora_pipeline.py:397-409; the CLIs pass
+    torch.Generator(device).manual_seed(seed), inference_lora.py:262,291), so a seed reproduces the reference's noise."""
+    from omg_b200 import factory
+    from omg_b200.config import UNetConfig
+    wl = factory.build_lora_workload(UNetConfig.tiny(), 256, 2, 8, 4, 7.5)
+    kw = dict(wl.call_kwargs)
+    for gdev in ("cpu", "cuda"):
+        a = wl.pipe(stage=1, generator=torch.Generator(gdev).manual_seed(14), **kw).images.clone()
+        wl.controller.reset()
+        lat0 = torch.randn((1, 4, 32, 32), generator=torch.Generator(gdev).manual_seed(14), device=gdev, dtype=torch.float16)
+        b = wl.pipe(stage=1, latents=lat0, **kw).images.clone()
+        wl.controller.reset()
+        assert torch.equal(a, b)
+    c = wl.pipe(stage=1, generator=torch.Generator("cuda").manual_seed(15), **kw).images
+    wl.controller.reset()
+    assert not torch.equal(a, c)
+
+
+def test_callback_on_step_end_sees_and_may_replace_latents():
+    """callback_on_step_end(pipe, i, t, {"latents": (2,4,h,w)}) after every scheduler step (lora_pipeline.py:617-625)."""
+    from omg_b200 import factory
+    from omg_b200.config import UNetConfig
+    wl = factory.build_lora_workload(UNetConfig.tiny(), 256, 2, 8, 4, 7.5)
+    kw = dict(wl.call_kwargs)
+    lat0 = torch.randn(1, 4, 32, 32, generator=torch.Generator().manual_seed(3)).half()
+    seen = []
+    out = wl.pipe(stage=1, latents=lat0, callback_on_step_end=lambda p, i, t, d: seen.append((i, float(t), d["latents"].clone())) or {},
+                  **kw).images
+    wl.controller.reset()
+    assert [s[0] for s in seen] == [0, 1, 2, 3] and seen[0][2].shape == (2, 4, 32, 32)
+    assert torch.equal(seen[-1][2].half(), out)
+    # replacing the latents after step 1 with the recorded ones is a no-op; replacing them with zeros is not
+    out2 = wl.pipe(stage=1, latents=lat0, callback_on_step_end=lambda p, i, t, d: {"latents": seen[i][2].clone()}, **kw).images
+    wl.controller.reset()
+    assert rel(out2, out) < 1e-3
+    out3 = wl.pipe(stage=1, latents=lat0, callback_on_step_end=lambda p, i, t, d: {"latents": torch.zeros_like(d["latents"])} if i == 1 else {},
+                   **kw).images
+    wl.controller.reset()
+    assert rel(out3, out) > 1e-2
