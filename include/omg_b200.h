@@ -87,6 +87,14 @@ typedef struct {
                              * group g multiplies with plane g (per-stream weights, e.g. W + s B_g A_g merged per concept) */
     int32_t cta_pair;   /* 0 = auto, 1 = single-CTA tiles, 2 = CTA pairs (cta_group::2, 256 x block_n tiles; block_n 256 | 160),
                          * 3 = tall tiles (one CTA, 256 x 160: two 128-row sub-tiles share each weight tile; block_n 160) */
+    /* GroupNorm statistics out of the producing GEMM / conv (ResnetBlock2D norm1/norm2, Transformer2DModel.norm,
+     * conv_norm_out [3P]): per image and per 32-pixel block of the output, the per-channel (sum, sum of squares) of the
+     * fp16-ROUNDED output values, written as float2 to col_stats_out [B][col_stats_rb_total][N]; this launch fills the
+     * blocks [col_stats_rb0, col_stats_rb0 + omg_gemm_colstats_blocks(W, H)) of every image.  The consuming
+     * omg_groupnorm_apply reduces them to (mean, rstd) per group - for any grouping, also over the channel
+     * concatenation of two producers - so GroupNorm never re-reads its input for statistics.  Not with GEGLU. */
+    void* col_stats_out;
+    int32_t col_stats_rb0, col_stats_rb_total;
 } omg_gemm_desc;
 
 int omg_gemm(const omg_gemm_desc* desc, void* stream);
@@ -94,6 +102,9 @@ int omg_gemm(const omg_gemm_desc* desc, void* stream);
 /* Tile plan omg_gemm will use for an output grid (W, H, B) with N channels: block_n and the number of row-statistics
  * partial planes this GEMM emits (= row_stats_parts for the consumer; two per n-tile). */
 int omg_gemm_plan(int N, int epilogue, int W, int H, int B, int* block_n, int* stats_parts);
+
+/* Number of 32-pixel column-statistics blocks one omg_gemm launch over an output grid (W, H) writes per image. */
+int omg_gemm_colstats_blocks(int W, int H);
 
 #define OMG_ATTN_MAX_ITEMS 16
 
@@ -134,6 +145,18 @@ int omg_attention(const omg_attn_desc* desc, void* stream);
 #define OMG_GN_WS_FLOATS(B) ((B) * 64 * (OMG_GN_MAX_SPLITS + 1))
 int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, const void* gamma, const void* beta,
                   float eps, int silu, void* stats_ws, void* y, void* stream);
+
+/* Per-channel (sum, sum of squares) partials of a stored channels-last tensor x [B, HW, C], one float2 per channel per
+ * 32-row block: out [B][ceil(HW/32)][C] - the layout omg_gemm's col_stats_out produces (for tensors that were modified
+ * after their producing GEMM, e.g. skip connections that received ControlNet residuals). */
+int omg_colstats(const void* x, int C, int B, int HW, void* out, void* stream);
+
+/* GroupNorm(32) [+ SiLU] of cat(x1 | x2) from per-channel partials (omg_gemm col_stats_out / omg_colstats): one tiny
+ * reduction launch (partials -> mean, rstd per image and group, fixed summation order) and one apply pass.
+ * part1 [B][rb1][C1] float2, part2 [B][rb2][C2] float2 (NULL when C2 == 0); stats_ws: B * 64 floats. */
+int omg_groupnorm_apply(const void* x1, int C1, const void* part1, int rb1, const void* x2, int C2, const void* part2,
+                        int rb2, int B, int HW, const void* gamma, const void* beta, float eps, int silu, void* stats_ws,
+                        void* y, void* stream);
 
 /* LayerNorm over the last dim of [rows, C] fp16 (BasicTransformerBlock norm1/2/3 [3P]). */
 int omg_layernorm(const void* x, const void* gamma, const void* beta, void* y, long long rows, int C, float eps,

@@ -63,6 +63,8 @@ struct alignas(64) GemmParams {
     int n_col_groups;          // c1/c2 are [n_col_groups][N]; row group g = rows [col_group_end[g-1], col_group_end[g])
     long long col_group_end[8];
     int w_group_rows;          // > 0: the weight matrix holds one [N, K] plane per row group (per-stream merged LoRA)
+    float4* col_stats;         // GroupNorm statistics of the output: [B][cs_rb_total][N] float2 (sum, sumsq), or null
+    int cs_rb0, cs_rb_total;
 };
 
 // CTAS = 2: a CTA pair (cluster of 2, cta_group::2) works on a 256 x BN tile; each CTA stages its own 128 A rows and
@@ -431,6 +433,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                     for (int j = 0; j < 16; ++j) outp[j] = pack_half2(v[2 * j], v[2 * j + 1]);
                 }
+                if constexpr (EPI != OMG_EPI_GEGLU) {
+                    if (p.col_stats != nullptr && !row_valid) {  // rows outside the image count as zeros
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) outp[j] = 0u;
+                    }
+                }
                 // this warp's staging buffer was last read by the TMA store of its previous chunk
                 if (lane == 0) tma_store_wait_read<0>();
                 __syncwarp();
@@ -447,6 +455,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     const int nout0 = (EPI == OMG_EPI_GEGLU) ? (nacc0 >> 1) : nacc0;
                     tma_store_4d(&p.d_map, sbuf, nout0, sw, sh, b);
                     tma_store_commit();
+                }
+                if constexpr (EPI != OMG_EPI_GEGLU) {
+                    if (p.col_stats != nullptr && b < p.img_b) {
+                        // per-channel (sum, sumsq) of the 32 rows x 32 channels just staged (the fp16-rounded values the
+                        // consumer GroupNorm will see): lane = (row parity, channel pair); 16 conflict-free LDS.32
+                        const int cp = lane & 15, hp = lane >> 4;
+                        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int r = 2 * i + hp;
+                            const __half2 h2 = *reinterpret_cast<const __half2*>(
+                                sbuf + r * 64 + (((cp >> 2) ^ (i & 3)) << 4) + ((cp & 3) << 2));
+                            const float2 f = __half22float2(h2);
+                            s0 += f.x;
+                            q0 = fmaf(f.x, f.x, q0);
+                            s1 += f.y;
+                            q1 = fmaf(f.y, f.y, q1);
+                        }
+                        s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+                        q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                        q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+                        const int col = nacc0 + 2 * cp;
+                        if (hp == 0 && col < p.N) {
+                            const size_t rb = (size_t)b * p.cs_rb_total + p.cs_rb0 + (size_t)rem * 4 + q;
+                            p.col_stats[(rb * p.N + col) >> 1] = make_float4(s0, q0, s1, q1);
+                        }
+                    }
                 }
             };
 #pragma unroll 1
@@ -583,6 +619,14 @@ extern "C" int omg_gemm_plan(int N, int epilogue, int W, int H, int B, int* bloc
     return 0;
 }
 
+extern "C" int omg_gemm_colstats_blocks(int W, int H) {
+    if (W < 1 || H < 1) return 0;
+    int tw = 128;
+    while (tw / 2 >= W && tw > 1) tw /= 2;
+    const int th = 128 / tw;
+    return ((W + tw - 1) / tw) * ((H + th - 1) / th) * 4;
+}
+
 extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     OMG_CHECK(d != nullptr, "omg_gemm: null descriptor");
@@ -654,6 +698,12 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     OMG_CHECK(!p.stats_in || (p.col_c1 && p.col_c2 && d->ln_dim > 0 && d->row_stats_parts >= 1 && !d->rowvec),
               "omg_gemm: folded LayerNorm needs col_c1, col_c2, ln_dim, row_stats_parts and no rowvec");
     OMG_CHECK(!p.stats_out || !geglu, "omg_gemm: row statistics cannot be emitted by the GEGLU epilogue");
+    p.col_stats = static_cast<float4*>(d->col_stats_out);
+    p.cs_rb0 = d->col_stats_rb0;
+    p.cs_rb_total = d->col_stats_rb_total;
+    OMG_CHECK(!p.col_stats || (!geglu && d->N % 32 == 0 && d->col_stats_rb0 >= 0 &&
+                               d->col_stats_rb0 + p.tiles_w * p.tiles_h * 4 <= d->col_stats_rb_total),
+              "omg_gemm: column statistics need a non-GEGLU epilogue, N %% 32 == 0 and rb0 + blocks <= rb_total");
     OMG_CHECK((!p.stats_out && !p.stats_in) || (d->d.sw == d->d.C && d->d.sh == (int64_t)d->d.sw * W && d->d.sb == d->d.sh * H),
               "omg_gemm: row statistics need a contiguous output view");
 

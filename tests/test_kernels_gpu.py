@@ -152,6 +152,28 @@ def test_self_attention(ops, B, N, heads):
     assert rel(out, ref) < 2e-3
 
 
+@pytest.mark.parametrize("n_q,n_kv,gain", [(256, 200, 1.0), (130, 321, 1.0), (512, 640, 2.5), (128, 129, 2.5),
+                                            (384, 1024, 3.0)])
+def test_attention_two_stream_edges(ops, n_q, n_kv, gain):
+    """The two-stream self-attention kernel (even / odd KV blocks, merged in the epilogue): odd block counts, a partial
+    last block, n_q != n_kv, and score ranges large enough that the lazy O rescale fires in both streams; with and
+    without `accumulate`."""
+    heads = 3
+    Cc = heads * 64
+    q = rnd(2, n_q, Cc, seed=11) * gain
+    kv = rnd(2, n_kv, 2 * Cc, seed=12)
+    kv[..., :Cc] *= gain
+    out = torch.empty(2, n_q, Cc, device="cuda", dtype=torch.float16)
+    items = [(0, 1, 1, 0), (1, 0, 0, 1)]  # out row 0 <- Q,K of row 1 with V of row 0, and vice versa
+    ops.attention(q, kv, kv, out, heads, n_q, n_kv, items, k_col0=0, v_col0=Cc)
+    ref = _attn_ref(q[[1, 0]], kv[[1, 0]][..., :Cc], kv[..., Cc:], heads, 0.125)
+    assert rel(out, ref) < 2e-3
+    base = rnd(2, n_q, Cc, seed=13)
+    out2 = base.clone()
+    ops.attention(q, kv, kv, out2, heads, n_q, n_kv, items, k_col0=0, v_col0=Cc, out_weight=0.5, accumulate=True)
+    assert rel(out2, base.float() + 0.5 * ref) < 2e-3
+
+
 def test_attention_p2p_remap_and_cross(ops):
     B, N, heads, Lk = 4, 1024, 10, 77
     Cc = heads * 64
