@@ -31,7 +31,8 @@ class GemmDesc(C.Structure):
                 ("residual_ld", C.c_int32), ("epilogue", C.c_int32), ("block_n", C.c_int32),
                 ("row_stats_out", C.c_void_p), ("row_stats_in", C.c_void_p), ("row_stats_parts", C.c_int32),
                 ("row_stats_stride", C.c_int64), ("ln_dim", C.c_int32), ("ln_eps", C.c_float), ("col_c1", C.c_void_p), ("col_c2", C.c_void_p),
-                ("n_col_groups", C.c_int32), ("col_group_end", C.c_int64 * 8), ("w_group_planes", C.c_int32), ("cta_pair", C.c_int32)]
+                ("n_col_groups", C.c_int32), ("col_group_end", C.c_int64 * 8), ("w_group_planes", C.c_int32), ("cta_pair", C.c_int32),
+                ("col_stats_out", C.c_void_p), ("col_stats_rb0", C.c_int32), ("col_stats_rb_total", C.c_int32)]
 
 
 class AttnDesc(C.Structure):
@@ -58,6 +59,11 @@ class FuseDesc(C.Structure):
 SYMBOLS = {
     "omg_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
     "omg_gemm_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "omg_gemm_colstats_blocks": (C.c_int, [C.c_int, C.c_int]),
+    "omg_colstats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "omg_groupnorm_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]),
     "omg_attention": (C.c_int, [C.POINTER(AttnDesc), C.c_void_p]),
     "omg_groupnorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

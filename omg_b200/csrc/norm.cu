@@ -181,6 +181,89 @@ __global__ void gn_apply_kernel(GnSrc s, int HW, int cpg, int silu, const float*
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// GroupNorm statistics from per-channel partials.  The producing GEMM / conv writes, per image and per 32-pixel block of
+// its output, the per-channel (sum, sum of squares) of the fp16-rounded values (gemm_tc.cu epilogue); omg_colstats
+// produces the same layout from a stored tensor.  gn_reduce_kernel turns them into (mean, rstd) per (image, group) for
+// ANY grouping of the channel concatenation (x1 | x2) - a decoder GroupNorm's groups straddle the hidden / skip
+// boundary - in a fixed summation order (deterministic, independent of the batch position).
+struct GnParts {
+    const float2* p1;
+    const float2* p2;
+    int C1, C2, rb1, rb2;
+};
+
+__global__ void gn_reduce_kernel(GnParts s, int cpg, float inv_n, float eps, float* __restrict__ stats) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const int g = blockIdx.x, b = blockIdx.y;
+    const int c_lo = g * cpg, c_hi = c_lo + cpg;
+    float sa = 0.f, sq = 0.f;
+    {   // channels of this group that live in source 1
+        const int lo = min(c_lo, s.C1), hi = min(c_hi, s.C1), n = hi - lo;
+        const float2* base = s.p1 + (size_t)b * s.rb1 * s.C1 + lo;
+        for (int idx = threadIdx.x; idx < n * s.rb1; idx += blockDim.x) {
+            const int rb = idx / n, k = idx - rb * n;
+            const float2 v = __ldg(base + (size_t)rb * s.C1 + k);
+            sa += v.x;
+            sq += v.y;
+        }
+    }
+    if (s.C2 > 0) {
+        const int lo = max(c_lo, s.C1) - s.C1, hi = max(c_hi, s.C1) - s.C1, n = hi - lo;
+        const float2* base = s.p2 + (size_t)b * s.rb2 * s.C2 + lo;
+        for (int idx = threadIdx.x; idx < n * s.rb2; idx += blockDim.x) {
+            const int rb = idx / n, k = idx - rb * n;
+            const float2 v = __ldg(base + (size_t)rb * s.C2 + k);
+            sa += v.x;
+            sq += v.y;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    __shared__ float2 red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = make_float2(sa, sq);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, q = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            a += red[w].x;
+            q += red[w].y;
+        }
+        const float mean = a * inv_n;
+        const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+        stats[((size_t)b * 32 + g) * 2] = mean;
+        stats[((size_t)b * 32 + g) * 2 + 1] = rsqrtf(var + eps);
+    }
+}
+
+// grid = (ceil(ceil(HW/32) / 8), B), block = 256: one warp per 32-row block; lane = channel pair, strided over C
+__global__ void colstats_kernel(const __half* __restrict__ x, int C, int HW, float2* __restrict__ out) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const int rbs = (HW + 31) / 32;
+    const int rb = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (rb >= rbs) return;
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int r0 = rb * 32, r1 = min(r0 + 32, HW);
+    const __half* xb = x + ((size_t)b * HW) * C;
+    for (int c = 2 * lane; c < C; c += 64) {
+        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+        for (int r = r0; r < r1; ++r) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(xb + (size_t)r * C + c));
+            s0 += f.x;
+            q0 = fmaf(f.x, f.x, q0);
+            s1 += f.y;
+            q1 = fmaf(f.y, f.y, q1);
+        }
+        float4* o = reinterpret_cast<float4*>(out + ((size_t)b * rbs + rb) * C + c);
+        *o = make_float4(s0, q0, s1, q1);
+    }
+}
+
 // One warp per token row; exact two-pass variance held in registers (C <= 2560).
 template <int MAX_VEC>
 __global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
@@ -292,6 +375,38 @@ extern "C" int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int
     OMG_CUDA(launch_pdl(gn_finalize_kernel, dim3(B), dim3(1024), 0, stream, (const float*)partial, splits,
                         1.0f / ((float)HW * (float)cpg), eps, stats));
     if (check_launch("gn_finalize_kernel")) return 1;
+    const size_t nvec = (size_t)HW * (C / 8);
+    OMG_CUDA(launch_pdl(gn_apply_kernel, dim3((unsigned)((nvec + 1023) / 1024), B), dim3(256), 0, stream, s, HW, cpg, silu,
+                        (const float*)stats, static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
+                        static_cast<__half*>(y)));
+    return check_launch("gn_apply_kernel");
+}
+
+extern "C" int omg_colstats(const void* x, int C, int B, int HW, void* out, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    OMG_CHECK(x && out, "omg_colstats: null pointer");
+    OMG_CHECK(C >= 8 && C % 8 == 0 && B >= 1 && HW >= 1, "omg_colstats: bad shape");
+    const int rbs = (HW + 31) / 32;
+    OMG_CUDA(launch_pdl(colstats_kernel, dim3((rbs + 7) / 8, B), dim3(256), 0, stream, static_cast<const __half*>(x), C, HW,
+                        static_cast<float2*>(out)));
+    return check_launch("colstats_kernel");
+}
+
+extern "C" int omg_groupnorm_apply(const void* x1, int C1, const void* part1, int rb1, const void* x2, int C2,
+                                   const void* part2, int rb2, int B, int HW, const void* gamma, const void* beta, float eps,
+                                   int silu, void* stats_ws, void* y, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    const int C = C1 + C2;
+    OMG_CHECK(x1 && part1 && gamma && beta && stats_ws && y, "omg_groupnorm_apply: null pointer");
+    OMG_CHECK(C1 > 0 && C1 % 8 == 0 && C2 >= 0 && C2 % 8 == 0 && (C2 == 0 || (x2 && part2)), "omg_groupnorm_apply: bad channel split");
+    OMG_CHECK(C % 32 == 0 && C <= 2560, "omg_groupnorm_apply: C=%d must be a multiple of 32 and <= 2560", C);
+    OMG_CHECK(B >= 1 && HW >= 1 && rb1 >= 1 && (C2 == 0 || rb2 >= 1), "omg_groupnorm_apply: empty input");
+    const int cpg = C / 32;
+    GnSrc s{static_cast<const __half*>(x1), static_cast<const __half*>(x2), C1, C2};
+    GnParts parts{static_cast<const float2*>(part1), static_cast<const float2*>(part2), C1, C2, rb1, rb2};
+    float* stats = static_cast<float*>(stats_ws);  // [B][32][2] mean, rstd
+    OMG_CUDA(launch_pdl(gn_reduce_kernel, dim3(32, B), dim3(256), 0, stream, parts, cpg, 1.0f / ((float)HW * (float)cpg), eps, stats));
+    if (check_launch("gn_reduce_kernel")) return 1;
     const size_t nvec = (size_t)HW * (C / 8);
     OMG_CUDA(launch_pdl(gn_apply_kernel, dim3((unsigned)((nvec + 1023) / 1024), B), dim3(256), 0, stream, s, HW, cpg, silu,
                         (const float*)stats, static_cast<const __half*>(gamma), static_cast<const __half*>(beta),

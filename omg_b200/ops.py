@@ -35,9 +35,12 @@ def _ptr(t):
 
 
 def gemm(a_views, segs, w, N, Ktot, d_view, bias=None, rowvec=None, rowvec_ld=0, residual=None, residual_ld=0,
-         epilogue=L.EPI_NONE, block_n=0, w2=None, stats_out=None, ln=None, cta_pair=0, row_groups=None):
+         epilogue=L.EPI_NONE, block_n=0, w2=None, stats_out=None, ln=None, cta_pair=0, row_groups=None, colstats=None):
     d = L.GemmDesc()
     d.cta_pair = cta_pair
+    if colstats is not None:  # (partials [B, rb_total, N, 2] fp32, first block this launch fills)
+        part, rb0 = colstats
+        d.col_stats_out, d.col_stats_rb0, d.col_stats_rb_total = part.data_ptr(), rb0, part.shape[1]
     if row_groups is not None:  # per-stream weight planes: w is [len(row_groups) * N, Ktot]
         d.w_group_planes = d.n_col_groups = len(row_groups)
         for i, e in enumerate(row_groups):
@@ -80,8 +83,13 @@ def gemm_plan(N, epilogue, W, H=1, B=1):
     return bn.value, nt.value
 
 
+def colstats_blocks(W, H=1):
+    """32-pixel column-statistics blocks one omg_gemm launch over an output grid (W, H) writes per image."""
+    return L.load().omg_gemm_colstats_blocks(W, H)
+
+
 def linear(x, w, bias=None, residual=None, out=None, epilogue=L.EPI_NONE, extra=None, block_n=0, lora=None,
-           stats_out=None, ln=None, cta_pair=0, row_groups=None):
+           stats_out=None, ln=None, cta_pair=0, row_groups=None, colstats=None):
     """out[M, N'] = epi(x[M,K] @ w[N, :K]^T (+ extra K-segments) + bias) + residual.
 
     `extra` = list of (tensor [M,Ki], column offset into w): further K-segments of the same weight matrix.
@@ -105,9 +113,12 @@ def linear(x, w, bias=None, residual=None, out=None, epilogue=L.EPI_NONE, extra=
         t, w2 = lora
         views.append(view4(t))
         segs.append((len(views) - 1, 0, 0, 0, t.shape[1], 0, 1))
+    # colstats: partials [B, rb, N, 2] of an output of B images x HW tokens; the [M, N] GEMM sees them as one image
+    # of M rows, which is the same memory when no 128-row tile straddles two images (HW % 128 == 0, caller's duty)
+    cs = None if colstats is None else (colstats.view(1, -1, colstats.shape[2], 2), 0)
     gemm(views, segs, w, N, Ktot, view4(out), bias=bias, residual=residual,
          residual_ld=0 if residual is None else residual.stride(0), epilogue=epilogue, block_n=block_n, w2=w2,
-         stats_out=stats_out, ln=ln, cta_pair=cta_pair, row_groups=row_groups)
+         stats_out=stats_out, ln=ln, cta_pair=cta_pair, row_groups=row_groups, colstats=cs)
     return out
 
 
@@ -115,7 +126,7 @@ def _taps3x3(Cin, a_idx=0, c0=0, k0=0):
     return [(a_idx, kx - 1, ky - 1, c0, Cin, k0 + (ky * 3 + kx) * Cin) for ky in range(3) for kx in range(3)]
 
 
-def conv3x3(x, w, bias=None, rowvec=None, residual=None, out=None, shortcut=None, block_n=0, cta_pair=0):
+def conv3x3(x, w, bias=None, rowvec=None, residual=None, out=None, shortcut=None, block_n=0, cta_pair=0, colstats=None):
     """3x3 / stride 1 / pad 1 conv over (B,H,W,Cin).  w = [N, 9*Cin (+ shortcut K)] packed (ky, kx, c).
 
     shortcut = list of (tensor (B,H,W,Ci), weight column offset): 1x1-conv K-segments added to the same accumulator
@@ -132,11 +143,12 @@ def conv3x3(x, w, bias=None, rowvec=None, residual=None, out=None, shortcut=None
         segs.append((len(views) - 1, 0, 0, 0, t.shape[3], off))
     gemm(views, segs, w, N, Ktot, view4(out), bias=bias, rowvec=rowvec,
          rowvec_ld=0 if rowvec is None else rowvec.stride(0),
-         residual=residual, residual_ld=0 if residual is None else N, block_n=block_n, cta_pair=cta_pair)
+         residual=residual, residual_ld=0 if residual is None else N, block_n=block_n, cta_pair=cta_pair,
+         colstats=None if colstats is None else (colstats, 0))
     return out
 
 
-def conv3x3_s2(x, w, bias=None, out=None, block_n=0):
+def conv3x3_s2(x, w, bias=None, out=None, block_n=0, colstats=None):
     """3x3 / stride 2 / pad 1 conv (Downsample2D): A operands are the four stride-2 phase views of x."""
     B, H, W, Cin = x.shape
     N, Ktot = w.shape
@@ -150,11 +162,12 @@ def conv3x3_s2(x, w, bias=None, out=None, block_n=0):
             py, oy = (1, -1) if ky == 0 else ((0, 0) if ky == 1 else (1, 0))
             px, ox = (1, -1) if kx == 0 else ((0, 0) if kx == 1 else (1, 0))
             segs.append((py * 2 + px, ox, oy, 0, Cin, (ky * 3 + kx) * Cin))
-    gemm(views, segs, w, N, Ktot, view4(out), bias=bias, block_n=block_n)
+    gemm(views, segs, w, N, Ktot, view4(out), bias=bias, block_n=block_n,
+         colstats=None if colstats is None else (colstats, 0))
     return out
 
 
-def upsample2x_conv3x3(x, w, bias=None, out=None, block_n=0):
+def upsample2x_conv3x3(x, w, bias=None, out=None, block_n=0, colstats=None):
     """nearest-2x upsample followed by 3x3 conv (Upsample2D) without materialising the upsampled tensor:
     each output phase (py,px) is a 9-tap conv over x with shifted taps, stored through a strided output view."""
     B, H, W, Cin = x.shape
@@ -166,7 +179,8 @@ def upsample2x_conv3x3(x, w, bias=None, out=None, block_n=0):
     for py in range(2):
         for px in range(2):
             segs = [(0, off[px][kx], off[py][ky], 0, Cin, (ky * 3 + kx) * Cin) for ky in range(3) for kx in range(3)]
-            gemm([xv], segs, w, N, Ktot, view4(out[:, py::2, px::2, :]), bias=bias, block_n=block_n)
+            cs = None if colstats is None else (colstats, (py * 2 + px) * colstats_blocks(W, H))
+            gemm([xv], segs, w, N, Ktot, view4(out[:, py::2, px::2, :]), bias=bias, block_n=block_n, colstats=cs)
     return out
 
 
@@ -205,6 +219,39 @@ def groupnorm(x1, gamma, beta, eps, silu, x2=None, out=None, stats_ws=None):
     L.check(L.load().omg_groupnorm(x1.data_ptr(), C1, _ptr(x2), C2, B, HW, gamma.data_ptr(), beta.data_ptr(),
                                    float(eps), int(silu), stats_ws.data_ptr(), out.data_ptr(), _stream()),
             "omg_groupnorm")
+    return out
+
+
+def colstats(x, out=None):
+    """Per-channel (sum, sumsq) partials of a stored (B, HW.., C) tensor, one per 32-row block: [B, ceil(HW/32), C, 2]."""
+    _chk16(x)
+    assert x.is_contiguous()
+    B, Cc = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * Cc)
+    if out is None:
+        out = torch.empty((B, (HW + 31) // 32, Cc, 2), dtype=torch.float32, device=x.device)
+    assert out.shape[0] >= B and out.shape[1] == (HW + 31) // 32 and out.shape[2] == Cc
+    L.check(L.load().omg_colstats(x.data_ptr(), Cc, B, HW, out.data_ptr(), _stream()), "omg_colstats")
+    return out
+
+
+def groupnorm_apply(x1, part1, gamma, beta, eps, silu, x2=None, part2=None, out=None, stats_ws=None):
+    """GroupNorm(32)(cat([x1, x2], channel)) [+ SiLU] with the statistics taken from per-channel partials
+    (omg_gemm colstats / ops.colstats): no statistics pass over x."""
+    _chk16(x1)
+    B, C1 = x1.shape[0], x1.shape[-1]
+    HW = x1.numel() // (B * C1)
+    C2 = 0 if x2 is None else x2.shape[-1]
+    assert x1.is_contiguous() and (x2 is None or x2.is_contiguous())
+    assert part1.shape[0] == B and part1.shape[2] == C1 and (x2 is None or (part2.shape[0] == B and part2.shape[2] == C2))
+    if out is None:
+        out = torch.empty((*x1.shape[:-1], C1 + C2), dtype=torch.float16, device=x1.device)
+    if stats_ws is None:
+        stats_ws = torch.empty(B * 64, dtype=torch.float32, device=x1.device)
+    L.check(L.load().omg_groupnorm_apply(x1.data_ptr(), C1, part1.data_ptr(), part1.shape[1], _ptr(x2), C2, _ptr(part2),
+                                         0 if part2 is None else part2.shape[1], B, HW, gamma.data_ptr(), beta.data_ptr(),
+                                         float(eps), int(silu), stats_ws.data_ptr(), out.data_ptr(), _stream()),
+            "omg_groupnorm_apply")
     return out
 
 

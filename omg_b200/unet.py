@@ -273,6 +273,8 @@ class UNetRunner:
         self.ln_fold = os.environ.get("OMG_LN_FOLD", "1") != "0"
         # LoRA streams of a grouped launch use per-stream merged weight planes (OMG_LORA=unmerged: K-segment path)
         self.merge_lora = os.environ.get("OMG_LORA", "merged") != "unmerged"
+        # GroupNorm statistics come out of the producing conv / GEMM epilogue (OMG_GN_FUSE=0: statistics pass per norm)
+        self.gn_fuse = os.environ.get("OMG_GN_FUSE", "1") != "0"
         self.dev = model.device
         self.ws: Dict[str, torch.Tensor] = {}
         self.use_graphs = use_graphs
@@ -323,6 +325,23 @@ class UNetRunner:
 
     def fbuf(self, name, shape) -> torch.Tensor:
         return self._alloc(name, shape, torch.float32, True)
+
+    def _cs(self, t: torch.Tensor, W: int, H: int, launches: int = 1):
+        """Column-statistics partials buffer for the GEMM output `t` over a per-image grid (W, H): the producing launch
+        fills it, the consuming GroupNorm finds it as `t._cs` (no statistics pass over t)."""
+        if not self.gn_fuse:
+            return None
+        rb = ops.colstats_blocks(W, H) * launches
+        part = self._alloc(f"cs.{t.data_ptr()}", (t.shape[0], rb, t.shape[-1], 2), torch.float32, False)
+        t._cs = part
+        return part
+
+    def _gn(self, x, gamma, beta, eps, silu, out, x2=None):
+        p1 = getattr(x, "_cs", None)
+        p2 = None if x2 is None else getattr(x2, "_cs", None)
+        if self.gn_fuse and p1 is not None and (x2 is None or p2 is not None):
+            return ops.groupnorm_apply(x, p1, gamma, beta, eps, silu, x2=x2, part2=p2, out=out, stats_ws=self.stats_ws)
+        return ops.groupnorm(x, gamma, beta, eps, silu, x2=x2, out=out, stats_ws=self.stats_ws)
 
     def _ln_vectors(self, key, groups, n, active):
         """c1 / c2 planes of the folded LayerNorm for every row group: the LoRA delta  s B (A' x)  is linear in the
@@ -385,7 +404,7 @@ class UNetRunner:
         return res
 
     def _lin(self, key, x2d, out, bias=None, residual=None, epilogue=L.EPI_NONE, groups=None, rows_per_item=None,
-             stats_out=None, ln=None):
+             stats_out=None, ln=None, colstats=None):
         """Linear with the un-merged LoRA deltas of every row group: t[rows_g, cols_g] = x[rows_g] A_g^T (skinny
         GEMMs, the other blocks of t stay zero), then ONE GEMM over all rows whose extra K-segment is t against
         [s B_1 | s B_2 | ...].  ln = (row statistics, parts, channels): the input's LayerNorm is folded into this
@@ -405,7 +424,7 @@ class UNetRunner:
             ln_arg = (stats, parts, M, 0, dim, 1e-5, c1, c2, ends)
         if not active:
             return ops.linear(x2d, w, bias=bias, residual=residual, out=out, epilogue=epilogue, stats_out=stats_out,
-                              ln=ln_arg)
+                              ln=ln_arg, colstats=colstats)
         base = groups[0].start
         ends = [(g.stop - base) * n for g in groups]
         if self.merge_lora and groups is self.groups and len(groups) <= 8 and all(e % 128 == 0 for e in ends[:-1]):
@@ -415,7 +434,7 @@ class UNetRunner:
             if ln is not None:
                 ln_arg = (ln[0], ln[1], M, 0, ln[2], 1e-5, c1m, c2m, ends)
             return ops.linear(x2d, wm, bias=bias, residual=residual, out=out, epilogue=epilogue, stats_out=stats_out,
-                              ln=ln_arg, row_groups=ends)
+                              ln=ln_arg, row_groups=ends, colstats=colstats)
         a_idx = 2 if ln is not None else 0   # gamma-folded A for LayerNorm consumers
         r_tot = sum(e[0].shape[0] for _, e in active)
         sig = ",".join(f"{g.start}-{g.stop}:{e[0].shape[0]}" for g, e in active)
@@ -432,7 +451,7 @@ class UNetRunner:
             ops.linear(x2d[r0:r1], e[a_idx], out=t[r0:r1, c0:c0 + e[0].shape[0]])
             c0 += e[0].shape[0]
         return ops.linear(x2d, w, bias=bias, residual=residual, out=out, epilogue=epilogue, lora=(t, b2),
-                          stats_out=stats_out, ln=ln_arg)
+                          stats_out=stats_out, ln=ln_arg, colstats=colstats)
 
     # ------------------------------------------------------------------------------------------- per-call setup
     def set_conditioning(self, timesteps, ctx, text_embeds: torch.Tensor, time_ids: torch.Tensor,
@@ -534,18 +553,18 @@ class UNetRunner:
         B, H, W, C1 = x.shape
         C2 = 0 if skip is None else skip.shape[3]
         cout = P[name + ".bias1"].shape[0]
-        a1 = ops.groupnorm(x, P[name + ".g1"], P[name + ".b1"], 1e-5, 1, x2=skip,
-                           out=self.buf(name + ".a1", (B, H, W, C1 + C2)), stats_ws=self.stats_ws)
+        a1 = self._gn(x, P[name + ".g1"], P[name + ".b1"], 1e-5, 1, self.buf(name + ".a1", (B, H, W, C1 + C2)), x2=skip)
         off = m.temb_off[name]
-        h = ops.conv3x3(a1, P[name + ".w1"], bias=P[name + ".bias1"], rowvec=self.temb_step[:, off:off + cout],
-                        out=self.buf(name + ".h", (B, H, W, cout)))
-        a2 = ops.groupnorm(h, P[name + ".g2"], P[name + ".b2"], 1e-5, 1, out=self.buf(name + ".a2", (B, H, W, cout)),
-                           stats_ws=self.stats_ws)
+        h = self.buf(name + ".h", (B, H, W, cout))
+        ops.conv3x3(a1, P[name + ".w1"], bias=P[name + ".bias1"], rowvec=self.temb_step[:, off:off + cout], out=h,
+                    colstats=self._cs(h, W, H))
+        a2 = self._gn(h, P[name + ".g2"], P[name + ".b2"], 1e-5, 1, self.buf(name + ".a2", (B, H, W, cout)))
         out = self.buf(name + ".out", (B, H, W, cout))
+        cs = self._cs(out, W, H)
         if P[name + ".w2"].shape[1] > 9 * cout:
             sc = [(x, 9 * cout)] + ([(skip, 9 * cout + C1)] if skip is not None else [])
-            return ops.conv3x3(a2, P[name + ".w2"], bias=P[name + ".bias2"], shortcut=sc, out=out)
-        return ops.conv3x3(a2, P[name + ".w2"], bias=P[name + ".bias2"], residual=x, out=out)
+            return ops.conv3x3(a2, P[name + ".w2"], bias=P[name + ".bias2"], shortcut=sc, out=out, colstats=cs)
+        return ops.conv3x3(a2, P[name + ".w2"], bias=P[name + ".bias2"], residual=x, out=out, colstats=cs)
 
     def _transformer(self, name, ch, layers, x, variant):
         P, m = self.m.p, self.m
@@ -554,8 +573,7 @@ class UNetRunner:
         M = B * N
         heads = ch // m.cfg.head_dim
         scale = m.cfg.head_dim ** -0.5
-        n = ops.groupnorm(x, P[name + ".norm.g"], P[name + ".norm.b"], 1e-6, 0, out=self.buf(f"tr.n.{ch}.{N}", (B, H, W, ch)),
-                          stats_ws=self.stats_ws)
+        n = self._gn(x, P[name + ".norm.g"], P[name + ".norm.b"], 1e-6, 0, self.buf(f"tr.n.{ch}.{N}", (B, H, W, ch)))
         h = self.buf(f"tr.h.{ch}.{N}", (M, ch))
         # LayerNorm fold: every GEMM that produces h also emits h's row statistics; the GEMMs that consume
         # LayerNorm(h) run on raw h.  Needs 128-row-aligned stream boundaries (tiles must not straddle streams).
@@ -598,7 +616,9 @@ class UNetRunner:
             self._lin(b + ".ff1", normed(b, "norm3"), g, bias=P[b + ".ff1.b"], epilogue=L.EPI_GEGLU, ln=lnS)
             self._lin(b + ".ff2", g, h, bias=P[b + ".ff2.b"], residual=h, stats_out=stats)
         out = self.buf(name + ".out", (B, H, W, ch))
-        self._lin(name + ".proj_out", h, out.view(M, ch), bias=P[name + ".proj_out.b"], residual=x.view(M, ch))
+        # the [M, ch] GEMM walks 128-token tiles: its per-32-row partials are per-image partials iff N % 128 == 0
+        cs = self._cs(out, N, 1) if N % 128 == 0 else None
+        self._lin(name + ".proj_out", h, out.view(M, ch), bias=P[name + ".proj_out.b"], residual=x.view(M, ch), colstats=cs)
         return out
 
     def _encoder(self, h, variant):
@@ -614,8 +634,8 @@ class UNetRunner:
                 skips.append(h)
             if i < nb - 1:
                 B, H, W, _ = h.shape
-                h = ops.conv3x3_s2(h, P[f"down{i}.w"], bias=P[f"down{i}.b"],
-                                   out=self.buf(f"down{i}.out", (B, H // 2, W // 2, ch)))
+                d = self.buf(f"down{i}.out", (B, H // 2, W // 2, ch))
+                h = ops.conv3x3_s2(h, P[f"down{i}.w"], bias=P[f"down{i}.b"], out=d, colstats=self._cs(d, W // 2, H // 2))
                 skips.append(h)
         ch = cfg.block_out_channels[-1]
         h = self._resblock("mid_block.resnets.0", h)
@@ -626,8 +646,8 @@ class UNetRunner:
     def _forward_unet(self, variant):
         m, cfg, P = self.m, self.m.cfg, self.m.p
         B, H, W = self.B, self.H, self.W
-        h = ops.conv3x3(self.sample_in, P["conv_in.w"], bias=P["conv_in.b"],
-                        out=self.buf("conv_in.out", (B, H, W, cfg.block_out_channels[0])))
+        h = self.buf("conv_in.out", (B, H, W, cfg.block_out_channels[0]))
+        ops.conv3x3(self.sample_in, P["conv_in.w"], bias=P["conv_in.b"], out=h, colstats=self._cs(h, W, H))
         h, skips = self._encoder(h, variant)
         if variant.get("residuals", False):
             # ControlNet outputs * conditioning_scale, added in place to the rows of the stream they belong to.  Several
@@ -640,6 +660,13 @@ class UNetRunner:
                 for sk, r in zip(skips + [h], list(down_r) + [mid_r]):
                     dst = sk[r0:r0 + r.shape[0]]
                     ops.axpy(dst, r, r_scale, out=dst)
+                    part = getattr(sk, "_cs", None)
+                    if part is not None:  # the producer's statistics no longer describe these images: recompute them
+                        hw = sk.shape[1] * sk.shape[2]
+                        if part.shape[1] == (hw + 31) // 32:
+                            ops.colstats(dst, out=part[r0:r0 + r.shape[0]])
+                        else:
+                            sk._cs = None
         nb = len(cfg.block_out_channels)
         for i in range(nb):
             ch, layers = cfg.block_out_channels[nb - 1 - i], cfg.transformer_layers[nb - 1 - i]
@@ -649,10 +676,9 @@ class UNetRunner:
                     h = self._transformer(f"up_blocks.{i}.attentions.{j}", ch, layers, h, variant)
             if i < nb - 1:
                 Bh, Hh, Wh, _ = h.shape
-                h = ops.upsample2x_conv3x3(h, P[f"up{i}.w"], bias=P[f"up{i}.b"],
-                                           out=self.buf(f"up{i}.out", (Bh, 2 * Hh, 2 * Wh, ch)))
-        a = ops.groupnorm(h, P["norm_out.g"], P["norm_out.b"], 1e-5, 1, out=self.buf("norm_out", tuple(h.shape)),
-                          stats_ws=self.stats_ws)
+                u = self.buf(f"up{i}.out", (Bh, 2 * Hh, 2 * Wh, ch))
+                h = ops.upsample2x_conv3x3(h, P[f"up{i}.w"], bias=P[f"up{i}.b"], out=u, colstats=self._cs(u, Wh, Hh, launches=4))
+        a = self._gn(h, P["norm_out.g"], P["norm_out.b"], 1e-5, 1, self.buf("norm_out", tuple(h.shape)))
         return ops.conv3x3(a, P["conv_out.w"], bias=P["conv_out.b"], out=self.buf("noise", (B, H, W, 8)))
 
     def _forward_controlnet(self, variant):
@@ -660,8 +686,9 @@ class UNetRunner:
         B, H, W = self.B, self.H, self.W
         c0 = cfg.block_out_channels[0]
         # sample = conv_in(sample) + cond_embedding: the embedding is the GEMM epilogue residual
-        h = ops.conv3x3(self.sample_in, P["conv_in.w"], bias=P["conv_in.b"], residual=self.cond_emb,
-                        out=self.buf("conv_in.out", (B, H, W, c0)))
+        h = self.buf("conv_in.out", (B, H, W, c0))
+        ops.conv3x3(self.sample_in, P["conv_in.w"], bias=P["conv_in.b"], residual=self.cond_emb, out=h,
+                    colstats=self._cs(h, W, H))
         h, skips = self._encoder(h, variant)
         outs = []
         for i, s in enumerate(skips):

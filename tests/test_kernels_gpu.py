@@ -399,3 +399,62 @@ def test_fuse_step_matches_the_reference_fusion_statements(ops):
     eps = d["noise_after_cfg"].permute(0, 2, 3, 1).reshape(2, HW, 4).cuda()
     ref = lat0 + eps * (sign - sig)
     assert rel(lat, ref) < 1e-5
+
+
+def _gn_ref(x, gamma, beta, eps, silu):
+    y = F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma.float(), beta.float(), eps)
+    return F.silu(y) if silu else y
+
+
+@pytest.mark.parametrize("B,H,W,C1,C2", [(2, 32, 32, 640, 320), (3, 16, 16, 320, 0), (1, 8, 8, 1280, 1280), (2, 4, 4, 64, 32)])
+def test_groupnorm_from_producer_column_statistics(ops, B, H, W, C1, C2):
+    """GroupNorm whose statistics come out of the producing conv / GEMM epilogues (per-channel partials of the
+    fp16-rounded outputs): convs with tall, single and partial tiles, the group boundaries of the concatenation
+    straddling the two sources (640 | 320 -> 30 channels per group), against torch.group_norm of the stored tensors."""
+    cin = 64
+    x = rnd(B, H, W, cin, seed=1)
+    w1 = rnd(C1, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=2)
+    y1 = torch.empty(B, H, W, C1, device="cuda", dtype=torch.float16)
+    p1 = torch.full((B, ops.colstats_blocks(W, H), C1, 2), float("nan"), device="cuda")
+    ops.conv3x3(x, ops.pack_conv3x3_weight(w1), bias=rnd(C1, seed=3), out=y1, colstats=p1)
+    tot = p1.sum(1)
+    assert torch.allclose(tot[..., 0], y1.float().sum((1, 2)), rtol=1e-3, atol=5e-2)
+    assert torch.allclose(tot[..., 1], (y1.float() ** 2).sum((1, 2)), rtol=1e-3, atol=5e-2)
+    # the stand-alone statistics kernel produces the same totals (and, for full tiles, the same blocks)
+    p1b = ops.colstats(y1)
+    assert torch.allclose(p1b.sum(1), tot, rtol=1e-4, atol=1e-2)
+    y2 = p2 = None
+    if C2:
+        w2 = rnd(C2, cin, scale=cin ** -0.5, seed=4)
+        y2 = torch.empty(B, H, W, C2, device="cuda", dtype=torch.float16)
+        if (H * W) % 128 == 0:  # token-major producer (Transformer2DModel.proj_out): [B*HW, C] GEMM, per-image partials
+            p2 = torch.full((B, ops.colstats_blocks(H * W, 1), C2, 2), float("nan"), device="cuda")
+            ops.linear(x.view(-1, cin), w2, out=y2.view(-1, C2), residual=rnd(B * H * W, C2, seed=5), colstats=p2)
+        else:
+            ops.linear(x.view(-1, cin), w2, out=y2.view(-1, C2))
+            p2 = ops.colstats(y2)
+    C = C1 + C2
+    gamma, beta = rnd(C, seed=6) * 0.2 + 1.0, rnd(C, seed=7) * 0.2
+    for silu in (0, 1):
+        out = ops.groupnorm_apply(y1, p1, gamma, beta, 1e-5, silu, x2=y2, part2=p2)
+        xin = y1 if y2 is None else torch.cat([y1, y2], dim=-1)
+        ref = _gn_ref(xin, gamma, beta, 1e-5, silu)
+        assert rel(out.permute(0, 3, 1, 2), ref) < 2e-3
+        old = ops.groupnorm(y1, gamma, beta, 1e-5, silu, x2=y2)   # statistics-pass variant: same result
+        assert rel(out, old.float()) < 1e-3
+
+
+def test_column_statistics_of_down_and_up_convs(ops):
+    B, H, W, C = 2, 16, 16, 128
+    x = rnd(B, H, W, C, seed=1)
+    wd = ops.pack_conv3x3_weight(rnd(C, C, 3, 3, scale=(9 * C) ** -0.5, seed=2))
+    d = torch.empty(B, H // 2, W // 2, C, device="cuda", dtype=torch.float16)
+    pd = torch.full((B, ops.colstats_blocks(W // 2, H // 2), C, 2), float("nan"), device="cuda")
+    ops.conv3x3_s2(x, wd, bias=rnd(C, seed=3), out=d, colstats=pd)
+    assert torch.allclose(pd.sum(1)[..., 0], d.float().sum((1, 2)), rtol=1e-3, atol=5e-2)
+    assert torch.allclose(pd.sum(1)[..., 1], (d.float() ** 2).sum((1, 2)), rtol=1e-3, atol=5e-2)
+    u = torch.empty(B, 2 * H, 2 * W, C, device="cuda", dtype=torch.float16)
+    pu = torch.full((B, 4 * ops.colstats_blocks(W, H), C, 2), float("nan"), device="cuda")
+    ops.upsample2x_conv3x3(x, wd, bias=rnd(C, seed=4), out=u, colstats=pu)
+    assert torch.allclose(pu.sum(1)[..., 0], u.float().sum((1, 2)), rtol=1e-3, atol=5e-2)
+    assert torch.allclose(pu.sum(1)[..., 1], (u.float() ** 2).sum((1, 2)), rtol=1e-3, atol=5e-2)
