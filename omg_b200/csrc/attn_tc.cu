@@ -431,37 +431,39 @@ __global__ void __launch_bounds__(Att2Cfg::THREADS, 2) attn2_tc_kernel(const __g
                     }
                 }
             }
-        } else if (warp == 1) {
-            if (lane == 0) {  // ------------------------------------------------------------ MMA issuer (both streams)
+        } else if (warp <= 2) {
+            // ------------------------------------------------------------ MMA issuers: warp 1 -> stream 0, warp 2 -> stream 1
+            // (one issuing thread for both streams would wait for their P buffers in block order and lock the two
+            // chains together; with an issuer each, one stream's MMA round trip overlaps the other's softmax)
+            if (lane == 0) {
+                const int s = warp - 1;
                 constexpr uint32_t idesc_s = umma_idesc_f16(128, ATT_BKV, false, false);
                 constexpr uint32_t idesc_o = umma_idesc_f16(128, ATT_D, false, true);
                 const uint64_t q_desc = umma_desc_sw128(smem_u32(q_smem), 1024, 16);
                 const uint64_t k_desc0 = umma_desc_sw128(smem_u32(kv_smem), 1024, 16);
                 const uint64_t v_desc0 = umma_desc_sw128(smem_u32(kv_smem + ATT_K_BYTES), 1024, 1024);
+                const uint32_t s_col = tmem_base + Cfg::S_COL0 + s * 64, o_col = tmem_base + Cfg::O_COL0 + s * 64;
                 auto issue_s = [&](int jb) {
                     const uint64_t kd = k_desc0 + (uint64_t)((jb % KVS) * ((2 * ATT_K_BYTES) >> 4));
 #pragma unroll
-                    for (int k = 0; k < ATT_D / 16; ++k)
-                        tc_mma_f16_ss(tmem_base + Cfg::S_COL0 + (jb & 1) * 64, q_desc + 2 * k, kd + 2 * k, idesc_s, k > 0);
-                    tc_commit(&s_full[jb & 1]);
+                    for (int k = 0; k < ATT_D / 16; ++k) tc_mma_f16_ss(s_col, q_desc + 2 * k, kd + 2 * k, idesc_s, k > 0);
+                    tc_commit(&s_full[s]);
                 };
                 auto wait_kv = [&](int jb) { mbar_wait(&kv_full[jb % KVS], (jb / KVS) & 1); };
                 mbar_wait(q_full, 0);
-                for (int jb = 0; jb < 2 && jb < nkv; ++jb) {
-                    wait_kv(jb);
+                if (s < nkv) {
+                    wait_kv(s);
                     tc_fence_after();
-                    issue_s(jb);
+                    issue_s(s);
                 }
-                for (int j = 0; j < nkv; ++j) {
-                    const int s = j & 1, i = j >> 1;
+                for (int j = s, i = 0; j < nkv; j += 2, ++i) {
                     mbar_wait(&p_full[s], i & 1);  // P_s(j) is in TMEM (over S_s)
                     tc_fence_after();
                     const uint64_t vd = v_desc0 + (uint64_t)((j % KVS) * ((2 * ATT_K_BYTES) >> 4));
 #pragma unroll
                     for (int k = 0; k < ATT_BKV / 16; ++k)
-                        tc_mma_f16_ts(tmem_base + Cfg::O_COL0 + s * 64, tmem_base + Cfg::S_COL0 + s * 64 + 8 * k, vd + 128 * k,
-                                      idesc_o, (i > 0 || k > 0) ? 1u : 0u);
-                    tc_commit(&kv_empty[j % KVS]);
+                        tc_mma_f16_ts(o_col, s_col + 8 * k, vd + 128 * k, idesc_o, (i > 0 || k > 0) ? 1u : 0u);
+                    tc_commit(&kv_empty[j % KVS]);  // K_j and V_j belong to this stream alone
                     if (j + 2 < nkv) {  // behind the P.V in issue order: S_s may be overwritten
                         wait_kv(j + 2);
                         tc_fence_after();
@@ -492,7 +494,7 @@ __global__ void __launch_bounds__(Att2Cfg::THREADS, 2) attn2_tc_kernel(const __g
             tc_fence_after();
             const int kv_left = p.n_kv - j * ATT_BKV;
             // ---- pass A: row maximum
-            float mx0 = -INFINITY, mx1 = -INFINITY;
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t sr[32];
@@ -504,12 +506,14 @@ __global__ void __launch_bounds__(Att2Cfg::THREADS, 2) attn2_tc_kernel(const __g
                         if (c * 32 + t >= kv_left) sr[t] = __float_as_uint(-INFINITY);
                 }
 #pragma unroll
-                for (int t = 0; t < 32; t += 4) {  // two independent chains
+                for (int t = 0; t < 32; t += 8) {  // four independent chains
                     mx0 = fmax3(mx0, __uint_as_float(sr[t]), __uint_as_float(sr[t + 1]));
                     mx1 = fmax3(mx1, __uint_as_float(sr[t + 2]), __uint_as_float(sr[t + 3]));
+                    mx2 = fmax3(mx2, __uint_as_float(sr[t + 4]), __uint_as_float(sr[t + 5]));
+                    mx3 = fmax3(mx3, __uint_as_float(sr[t + 6]), __uint_as_float(sr[t + 7]));
                 }
             }
-            const float m_cand = fmaxf(m, fmaxf(mx0, mx1) * p.scale_log2);
+            const float m_cand = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2);
             if (i == 0) {
                 m = m_cand;
             } else {
@@ -624,6 +628,257 @@ __global__ void __launch_bounds__(Att2Cfg::THREADS, 2) attn2_tc_kernel(const __g
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Cross-attention (77 text keys, 16 IP-adapter keys, <= 128 keys in general): the whole key sequence is ONE block, so a
+// head needs one Q.K^T, one softmax and one P.V.  Launched as one CTA per (query tile, head) - 640 CTAs of ~3 us at
+// N = 1024 - the old kernel spent most of its time in per-CTA setup (barrier init, TMEM allocation, pipeline fill):
+// 22-35 us per launch for ~3 us of HBM traffic.  Here a CTA walks a GROUP of heads of its 128-query tile: Q_h / K_h / V_h
+// of the next head are fetched by TMA while the current head is in its softmax, the TMEM allocation and the barriers
+// live for the whole group, and the two co-resident CTAs of an SM fill each other's bubbles.
+//   NK = padded key count (16 | 80 | 128): S is 128 x NK fp32 in TMEM, P (fp16 pairs) overwrites it in place,
+//   O is 128 x 64.  256 TMEM columns per CTA, two CTAs per SM.
+template <int NK>
+struct AttXCfg {
+    static constexpr int THREADS = 256;
+    static constexpr int STAGES = 2;
+    static constexpr int KV_BYTES = NK * ATT_D * 2;
+    static constexpr int STAGE_BYTES = ATT_Q_BYTES + 2 * ((KV_BYTES + 1023) / 1024 * 1024);
+    static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + 256;
+    static constexpr int TMEM_COLS = 256;
+    static constexpr int O_COL0 = 128;
+};
+
+template <int NK>
+__global__ void __launch_bounds__(256, 2) attn_cross_kernel(const __grid_constant__ AttnParams p, int heads_per_cta) {
+    using Cfg = AttXCfg<NK>;
+    constexpr int KV_PAD = (Cfg::KV_BYTES + 1023) / 1024 * 1024;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full = bars;                    // [stage] Q, K, V of a head have landed
+    uint64_t* empty = bars + Cfg::STAGES;     // [stage] both MMAs of that head have completed
+    uint64_t* s_full = empty + Cfg::STAGES;   // scores ready
+    uint64_t* p_full = s_full + 1;            // probabilities written (and the previous head's O read out)
+    uint64_t* o_full = p_full + 1;            // P.V complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int slab = blockIdx.x, item = blockIdx.z;
+    const int h0 = blockIdx.y * heads_per_cta;
+    const int nh = min(heads_per_cta, p.heads - h0);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.q_map);
+        tma_prefetch_desc(&p.k_map);
+        tma_prefetch_desc(&p.v_map);
+        for (int i = 0; i < Cfg::STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 4);
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();
+    griddep_wait();
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == 0) {
+            if (lane == 0) {  // ------------------------------------------------------------ TMA producer
+                const int qb = p.q_b[item], kb = p.k_b[item], vb = p.v_b[item];
+                for (int i = 0; i < nh; ++i) {
+                    const int st = i % Cfg::STAGES;
+                    mbar_wait(&empty[st], ((i / Cfg::STAGES) & 1) ^ 1);
+                    uint8_t* base = smem + st * Cfg::STAGE_BYTES;
+                    const int col = (h0 + i) * ATT_D;
+                    mbar_arrive_expect_tx(&full[st], ATT_Q_BYTES + 2 * Cfg::KV_BYTES);
+                    tma_load_3d(base, &p.q_map, &full[st], p.q_col0 + col, slab * ATT_BQ, qb);
+                    tma_load_3d(base + ATT_Q_BYTES, &p.k_map, &full[st], p.k_col0 + col, 0, kb);
+                    tma_load_3d(base + ATT_Q_BYTES + KV_PAD, &p.v_map, &full[st], p.v_col0 + col, 0, vb);
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {  // ------------------------------------------------------------ MMA issuer
+                constexpr uint32_t idesc_s = umma_idesc_f16(128, NK, false, false);
+                constexpr uint32_t idesc_o = umma_idesc_f16(128, ATT_D, false, true);
+                for (int i = 0; i < nh; ++i) {
+                    const int st = i % Cfg::STAGES;
+                    const uint32_t base = smem_u32(smem + st * Cfg::STAGE_BYTES);
+                    const uint64_t q_desc = umma_desc_sw128(base, 1024, 16);
+                    const uint64_t k_desc = umma_desc_sw128(base + ATT_Q_BYTES, 1024, 16);
+                    const uint64_t v_desc = umma_desc_sw128(base + ATT_Q_BYTES + KV_PAD, 1024, 1024);
+                    mbar_wait(&full[st], (i / Cfg::STAGES) & 1);
+                    tc_fence_after();
+                    // behind the previous head's P.V in issue order, so its P (aliased on S) has been consumed
+#pragma unroll
+                    for (int k = 0; k < ATT_D / 16; ++k) tc_mma_f16_ss(tmem_base, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
+                    tc_commit(s_full);
+                    mbar_wait(p_full, i & 1);  // P_i in TMEM; the softmax group has also finished reading O_(i-1)
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < NK / 16; ++k)
+                        tc_mma_f16_ts(tmem_base + Cfg::O_COL0, tmem_base + 8 * k, v_desc + 128 * k, idesc_o, k > 0 ? 1u : 0u);
+                    tc_commit(o_full);
+                    tc_commit(&empty[st]);
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------------------------- softmax + epilogue
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t s_tmem = tmem_base + lane_base;
+        const uint32_t o_tmem = tmem_base + Cfg::O_COL0 + lane_base;
+        const int qrow = slab * ATT_BQ + row;
+        const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2);
+        for (int i = 0; i < nh; ++i) {
+            mbar_wait(s_full, i & 1);
+            tc_fence_after();
+            constexpr int NCH = (NK + 31) / 32;
+            uint32_t sr[NCH][32];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                if (NK - c * 32 >= 32) {
+                    tmem_ld_32x32(s_tmem + c * 32, sr[c]);
+                } else {
+                    uint32_t t16[16];
+                    tmem_ld_32x16(s_tmem + c * 32, t16);
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) sr[c][t] = t16[t];
+                }
+            }
+            tc_wait_ld();
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int t = 0; t < 32; ++t)
+                    if (c * 32 + t < NK) {
+                        if (c * 32 + t >= p.n_kv) sr[c][t] = __float_as_uint(-INFINITY);
+                        mx = fmaxf(mx, __uint_as_float(sr[c][t]));
+                    }
+            const float m = mx * p.scale_log2;
+            const uint64_t negm2 = pack_f32x2(-m, -m);
+            uint64_t sum2 = pack_f32x2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int npair = (NK - c * 32 >= 32) ? 16 : (NK - c * 32) / 2;
+                uint32_t pk[16];
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    if (t < npair) {
+                        const uint64_t x2 = ffma2(pack_f32x2(__uint_as_float(sr[c][2 * t]), __uint_as_float(sr[c][2 * t + 1])), scale2, negm2);
+                        float x0, x1;
+                        unpack_f32x2(x2, x0, x1);
+                        const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);  // exp2(-inf) = 0 for the masked keys
+                        sum2 = fadd2(sum2, pack_f32x2(p0, p1));
+                        pk[t] = pack_half2(p0, p1);
+                    } else {
+                        pk[t] = 0u;
+                    }
+                }
+                if (npair == 16) {
+                    tmem_st_32x16(s_tmem + c * 16, pk);
+                } else {
+                    uint32_t p8[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) p8[t] = pk[t];
+                    tmem_st_32x8(s_tmem + c * 16, p8);
+                }
+            }
+            float l, l_hi;
+            unpack_f32x2(sum2, l, l_hi);
+            l += l_hi;
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+            mbar_wait(o_full, i & 1);
+            tc_fence_after();
+            float o_acc[ATT_D];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(o_tmem + c * 32, r);
+                tc_wait_ld();
+#pragma unroll
+                for (int t = 0; t < 32; ++t) o_acc[c * 32 + t] = __uint_as_float(r[t]);
+            }
+            if (qrow < p.n_q) {
+                const float inv = p.out_weight / l;
+                __half* op = p.out + (long long)p.out_b[item] * p.out_bs + (long long)qrow * p.out_ld + p.out_col0 +
+                             (h0 + i) * ATT_D;
+                uint4* op4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = o_acc[t * 8 + e] * inv;
+                    if (p.accumulate) {
+                        const uint4 u = op4[t];
+                        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __half22float2(h2[e]);
+                            v[2 * e] += f.x;
+                            v[2 * e + 1] += f.y;
+                        }
+                    }
+                    op4[t] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
+                                        pack_half2(v[6], v[7]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int NK>
+static int launch_cross(AttnParams& p, const omg_attn_desc* d, cudaStream_t stream, int max_qb, int max_kb, int max_vb) {
+    static bool configured = false;
+    if (!configured) {
+        OMG_CUDA(cudaFuncSetAttribute(attn_cross_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttXCfg<NK>::SMEM));
+        configured = true;
+    }
+    (void)max_qb;
+    const int cols = d->heads * 64;
+    // K / V boxes cover the whole (padded) key sequence; rows beyond n_kv are zero-filled by TMA and masked
+    {
+        const uint64_t dims[3] = {(uint64_t)(d->k_col0 + cols), (uint64_t)d->n_kv, (uint64_t)(max_kb + 1)};
+        const uint64_t strides[3] = {1, (uint64_t)d->k_ld, (uint64_t)d->k_bs};
+        const uint32_t box[3] = {64, NK, 1};
+        if (make_tmap_f16(&p.k_map, d->k, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    }
+    {
+        const uint64_t dims[3] = {(uint64_t)(d->v_col0 + cols), (uint64_t)d->n_kv, (uint64_t)(max_vb + 1)};
+        const uint64_t strides[3] = {1, (uint64_t)d->v_ld, (uint64_t)d->v_bs};
+        const uint32_t box[3] = {64, NK, 1};
+        if (make_tmap_f16(&p.v_map, d->v, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    }
+    // heads per CTA: as many as keep the grid at >= ~1.5 CTAs per SM slot pair (148 SMs x 2), at most 8
+    const int tiles = ((d->n_q + ATT_BQ - 1) / ATT_BQ) * d->n_items;
+    int hpc = 1;
+    while (hpc < 8 && hpc * 2 <= d->heads && (long)tiles * ((d->heads + 2 * hpc - 1) / (2 * hpc)) >= 148) hpc *= 2;
+    if (d->heads % 5 == 0 && hpc == 4 && (long)tiles * (d->heads / 5) >= 128) hpc = 5;  // 10 / 20 heads: 5 per CTA, no tail group
+    dim3 grid((d->n_q + ATT_BQ - 1) / ATT_BQ, (d->heads + hpc - 1) / hpc, d->n_items);
+    OMG_CUDA(launch_pdl(attn_cross_kernel<NK>, grid, dim3(256), AttXCfg<NK>::SMEM, stream, p, hpc));
+    return check_launch("attn_cross_kernel");
+}
+
 static int make_attn_map(CUtensorMap* m, const void* ptr, int cols, int ld, int tokens, long long bs, int nb,
                          uint32_t box_rows) {
     const uint64_t dims[3] = {(uint64_t)cols, (uint64_t)tokens, (uint64_t)nb};
@@ -649,6 +904,7 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
     static bool configured = false;
     static int force_g = 0;
     static int two_stream_min_kv = 2 * ATT_BKV + 1;
+    static bool cross_kernel = true;
     if (!configured) {
         OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1, 3>::SMEM));
         OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1, 5>::SMEM));
@@ -656,6 +912,8 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
         OMG_CUDA(cudaFuncSetAttribute(attn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Att2Cfg::SMEM));
         const char* e = getenv("OMG_ATTN_TILES");  // 1 | 2: force the tiles-per-CTA variant (measurements)
         force_g = e ? atoi(e) : 0;
+        const char* e3 = getenv("OMG_ATTN_CROSS");  // 0: cross-attention through the per-(tile, head) kernel
+        cross_kernel = !(e3 && atoi(e3) == 0);
         const char* e2 = getenv("OMG_ATTN_STREAMS");  // 1: single-stream kernels only; 2 (default): two-stream self-attention
         two_stream_min_kv = (e2 && atoi(e2) == 1) ? (1 << 30) : (e2 && atoi(e2) == 3) ? 1 : 2 * ATT_BKV + 1;
         configured = true;
@@ -697,6 +955,11 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
     // stages each: 604 vs 569 TFLOP/s at N = 4096, 388 vs 362 at N = 1024).  Short key sequences (cross-attention,
     // one or two KV blocks) take the 3-stage variant: less shared memory to set up per CTA.
     const int tiles = force_g ? force_g : 1;
+    if (!force_g && cross_kernel && d->n_kv <= 128) {
+        if (d->n_kv <= 16) return launch_cross<16>(p, d, stream, max_qb, max_kb, max_vb);
+        if (d->n_kv <= 80) return launch_cross<80>(p, d, stream, max_qb, max_kb, max_vb);
+        return launch_cross<128>(p, d, stream, max_qb, max_kb, max_vb);
+    }
     if (!force_g && d->n_kv >= two_stream_min_kv) {
         dim3 grid((d->n_q + ATT_BQ - 1) / ATT_BQ, d->heads, d->n_items);
         OMG_CUDA(launch_pdl(attn2_tc_kernel, grid, dim3(Att2Cfg::THREADS), Att2Cfg::SMEM, stream, p));

@@ -174,6 +174,26 @@ def test_attention_two_stream_edges(ops, n_q, n_kv, gain):
     assert rel(out2, base.float() + 0.5 * ref) < 2e-3
 
 
+@pytest.mark.parametrize("B,n_q,n_kv,heads", [(4, 1024, 77, 20), (2, 4096, 77, 10), (2, 200, 16, 3), (1, 128, 128, 7),
+                                              (2, 300, 100, 5), (1, 64, 5, 1), (8, 1024, 77, 20)])
+def test_cross_attention_head_group_kernel(ops, B, n_q, n_kv, heads):
+    """Cross-attention kernel (one key block, a CTA walks a group of heads): text keys (77), IP tokens (16), padded key
+    counts, ragged query tiles, head counts with a tail group; remapped rows and the accumulate / out_weight term."""
+    Cc = heads * 64
+    q = rnd(B, n_q, Cc, seed=21)
+    kv = rnd(B + 1, n_kv, 2 * Cc, seed=22)
+    out = torch.empty(B, n_q, Cc, device="cuda", dtype=torch.float16)
+    items = [(b, (b + 1) % B, b + 1, b) for b in range(B)]
+    ops.attention(q, kv, kv, out, heads, n_q, n_kv, items, k_col0=0, v_col0=Cc)
+    qi = [(b + 1) % B for b in range(B)]
+    ref = _attn_ref(q[qi], kv[[b + 1 for b in range(B)]][..., :Cc], kv[:B][..., Cc:], heads, 0.125)
+    assert rel(out, ref) < 2e-3
+    base = rnd(B, n_q, Cc, seed=23)
+    out2 = base.clone()
+    ops.attention(q, kv, kv, out2, heads, n_q, n_kv, items, k_col0=0, v_col0=Cc, out_weight=0.8, accumulate=True)
+    assert rel(out2, base.float() + 0.8 * ref) < 2e-3
+
+
 def test_attention_p2p_remap_and_cross(ops):
     B, N, heads, Lk = 4, 1024, 10, 77
     Cc = heads * 64
