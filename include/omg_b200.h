@@ -142,7 +142,7 @@ int omg_attention(const omg_attn_desc* desc, void* stream);
  * ResnetBlock2D / Transformer2DModel / UNet up-blocks [3P] (call site src/pipelines/lora_pipeline.py:546-566).
  */
 #define OMG_GN_MAX_SPLITS 256
-#define OMG_GN_WS_FLOATS(B) ((B) * 64 * (OMG_GN_MAX_SPLITS + 1))
+#define OMG_GN_WS_FLOATS(B) ((B) * (2 * 2 * 2560 + 64 * OMG_GN_MAX_SPLITS))
 int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, const void* gamma, const void* beta,
                   float eps, int silu, void* stats_ws, void* y, void* stream);
 
@@ -153,7 +153,7 @@ int omg_colstats(const void* x, int C, int B, int HW, void* out, void* stream);
 
 /* GroupNorm(32) [+ SiLU] of cat(x1 | x2) from per-channel partials (omg_gemm col_stats_out / omg_colstats): one tiny
  * reduction launch (partials -> mean, rstd per image and group, fixed summation order) and one apply pass.
- * part1 [B][rb1][C1] float2, part2 [B][rb2][C2] float2 (NULL when C2 == 0); stats_ws: B * 64 floats. */
+ * part1 [B][rb1][C1] float2, part2 [B][rb2][C2] float2 (NULL when C2 == 0); stats_ws: OMG_GN_WS_FLOATS(B) floats. */
 int omg_groupnorm_apply(const void* x1, int C1, const void* part1, int rb1, const void* x2, int C2, const void* part2,
                         int rb2, int B, int HW, const void* gamma, const void* beta, float eps, int silu, void* stats_ws,
                         void* y, void* stream);

@@ -903,7 +903,7 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
               "omg_attention: output must be 16 B aligned per row");
     static bool configured = false;
     static int force_g = 0;
-    static int two_stream_min_kv = 2 * ATT_BKV + 1;
+    static int two_stream_min_kv = 1 << 30;
     static bool cross_kernel = true;
     if (!configured) {
         OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1, 3>::SMEM));
@@ -914,8 +914,10 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
         force_g = e ? atoi(e) : 0;
         const char* e3 = getenv("OMG_ATTN_CROSS");  // 0: cross-attention through the per-(tile, head) kernel
         cross_kernel = !(e3 && atoi(e3) == 0);
-        const char* e2 = getenv("OMG_ATTN_STREAMS");  // 1: single-stream kernels only; 2 (default): two-stream self-attention
-        two_stream_min_kv = (e2 && atoi(e2) == 1) ? (1 << 30) : (e2 && atoi(e2) == 3) ? 1 : 2 * ATT_BKV + 1;
+        // OMG_ATTN_STREAMS=2: self-attention through the two-stream kernel (measured slower than the single-stream kernel
+        // with double-buffered scores: 526-550 vs 610 TFLOP/s at N = 4096, 338-355 vs 396 at N = 1024; kept for measurements)
+        const char* e2 = getenv("OMG_ATTN_STREAMS");
+        two_stream_min_kv = (e2 && atoi(e2) == 2) ? 2 * ATT_BKV + 1 : (1 << 30);
         configured = true;
     }
     AttnParams p;

@@ -99,8 +99,20 @@ __global__ void gn_partial_kernel(GnSrc s, int HW, int cpg, int rows_per_cta, fl
     }
 }
 
+// per-(image, channel) affine of the normalisation: y = a * x + b with a = rstd * gamma, b = beta - mean * a
+__device__ __forceinline__ void gn_write_affine(float2* __restrict__ ab, int b, int C, int g, int cpg, int k0, int kstep,
+                                                float mean, float rstd, const __half* __restrict__ gamma,
+                                                const __half* __restrict__ beta) {
+    for (int k = k0; k < cpg; k += kstep) {
+        const int c = g * cpg + k;
+        const float a = rstd * __half2float(gamma[c]);
+        ab[(size_t)b * C + c] = make_float2(a, __half2float(beta[c]) - mean * a);
+    }
+}
+
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int splits, float inv_n, float eps,
-                                   float* __restrict__ stats) {
+                                   float2* __restrict__ ab, int C, int cpg, const __half* __restrict__ gamma,
+                                   const __half* __restrict__ beta) {
     const int b = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;  // block = 32 groups x 32 lanes
     griddep_launch_dependents();
     griddep_wait();
@@ -115,70 +127,81 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int splits
         sa += __shfl_xor_sync(0xffffffffu, sa, o);
         sq += __shfl_xor_sync(0xffffffffu, sq, o);
     }
-    if (lane == 0) {
-        const float mean = sa * inv_n;
-        const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
-        stats[((size_t)b * 32 + g) * 2] = mean;
-        stats[((size_t)b * 32 + g) * 2 + 1] = rsqrtf(var + eps);
-    }
+    const float mean = sa * inv_n;  // every lane holds the totals after the butterfly
+    const float rstd = rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.f) + eps);
+    gn_write_affine(ab, b, C, g, cpg, lane, 32, mean, rstd, gamma, beta);
 }
 
-// grid = (ceil(HW*C/8 / (256*4)), B): four 16 B vectors per thread, grid-strided so that every load instruction of a
-// warp is one contiguous 512 B run; all four loads are issued before any arithmetic
-__global__ void gn_apply_kernel(GnSrc s, int HW, int cpg, int silu, const float* __restrict__ stats,
-                                const __half* __restrict__ gamma, const __half* __restrict__ beta,
+// Apply pass: y = silu?(a[b, c] * x + b[b, c]).  block = (C/8 channel vectors, ry rows), grid = (row chunks, B): a thread
+// keeps ONE channel vector for all of its rows, so the affine is loaded once into registers and there is no index
+// arithmetic in the loop; four 16 B loads are in flight per thread, a warp's loads are contiguous runs of the row.
+__global__ void gn_apply_kernel(GnSrc s, int HW, int rows_per_cta, int silu, const float2* __restrict__ ab,
                                 __half* __restrict__ y) {
     griddep_launch_dependents();
     griddep_wait();
     const int C = s.C1 + s.C2;
-    const int vec_per_row = C / 8;
     const int b = blockIdx.y;
-    const size_t total = (size_t)HW * vec_per_row;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const size_t idx0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint4 u[4];
-    size_t rr[4];
-    int cc[4];
+    const int c0 = threadIdx.x * 8;
+    float a[8], sft[8];
+    {
+        const float4* p4 = reinterpret_cast<const float4*>(ab + (size_t)b * C + c0);
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        const size_t idx = idx0 + v * stride;
-        if (idx < total) {
-            rr[v] = idx / vec_per_row;
-            cc[v] = (int)(idx - rr[v] * vec_per_row) * 8;
-            u[v] = gn_load8(s, (size_t)b * HW + rr[v], cc[v]);
+        for (int i = 0; i < 4; ++i) {
+            const float4 v = __ldg(p4 + i);
+            a[2 * i] = v.x;
+            sft[2 * i] = v.y;
+            a[2 * i + 1] = v.z;
+            sft[2 * i + 1] = v.w;
         }
     }
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(r0 + rows_per_cta, HW);
+    const int step = blockDim.y;
+    auto emit = [&](const uint4& u, int r) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+        float v[8];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        if (idx0 + v * stride >= total) break;
-        const int c0 = cc[v];
-        const uint4 gw = *reinterpret_cast<const uint4*>(gamma + c0);
-        const uint4 bw = *reinterpret_cast<const uint4*>(beta + c0);
-        const __half* xh = reinterpret_cast<const __half*>(&u[v]);
-        const __half* gh = reinterpret_cast<const __half*>(&gw);
-        const __half* bh = reinterpret_cast<const __half*>(&bw);
-        int g = c0 / cpg;
-        int rem = c0 - g * cpg;
-        float mean = stats[((size_t)b * 32 + g) * 2], rstd = stats[((size_t)b * 32 + g) * 2 + 1];
-        float out[8];
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h2[i]);
+            v[2 * i] = fmaf(a[2 * i], f.x, sft[2 * i]);
+            v[2 * i + 1] = fmaf(a[2 * i + 1], f.y, sft[2 * i + 1]);
+        }
+        if (silu) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float val = (__half2float(xh[i]) - mean) * rstd * __half2float(gh[i]) + __half2float(bh[i]);
-            if (silu) val = val / (1.0f + __expf(-val));
-            out[i] = val;
-            if (++rem == cpg && i < 7) {
-                rem = 0;
-                ++g;
-                mean = stats[((size_t)b * 32 + g) * 2];
-                rstd = stats[((size_t)b * 32 + g) * 2 + 1];
-            }
+            for (int i = 0; i < 8; ++i) v[i] = __fdividef(v[i], 1.0f + __expf(-v[i]));
         }
         uint4 o;
         __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(out[2 * i], out[2 * i + 1]);
-        *reinterpret_cast<uint4*>(y + ((size_t)b * HW + rr[v]) * C + c0) = o;
+        for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(y + ((size_t)b * HW + r) * C + c0) = o;
+    };
+    int r = r0 + threadIdx.y;
+    for (; r + 3 * step < r1; r += 4 * step) {
+        const uint4 u0 = gn_load8(s, (size_t)b * HW + r, c0);
+        const uint4 u1 = gn_load8(s, (size_t)b * HW + r + step, c0);
+        const uint4 u2 = gn_load8(s, (size_t)b * HW + r + 2 * step, c0);
+        const uint4 u3 = gn_load8(s, (size_t)b * HW + r + 3 * step, c0);
+        emit(u0, r);
+        emit(u1, r + step);
+        emit(u2, r + 2 * step);
+        emit(u3, r + 3 * step);
     }
+    for (; r < r1; r += step) emit(gn_load8(s, (size_t)b * HW + r, c0), r);
+}
+
+static int launch_gn_apply(const GnSrc& s, int B, int HW, int silu, const float2* ab, __half* y, cudaStream_t stream) {
+    const int C = s.C1 + s.C2;
+    const int tx = C / 8;
+    int ty = 512 / tx;
+    if (ty < 1) ty = 1;
+    if (ty > 16) ty = 16;
+    // ~2 CTAs per SM slot at batch 4 (the row partition depends on (HW, C) only); at least 4 rows per thread
+    int rows_per_cta = (HW + 63) / 64;
+    if (rows_per_cta < 4 * ty) rows_per_cta = 4 * ty;
+    const int chunks = (HW + rows_per_cta - 1) / rows_per_cta;
+    OMG_CUDA(launch_pdl(gn_apply_kernel, dim3(chunks, B), dim3(tx, ty), 0, stream, s, HW, rows_per_cta, silu, ab, y));
+    return check_launch("gn_apply_kernel");
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -193,51 +216,63 @@ struct GnParts {
     int C1, C2, rb1, rb2;
 };
 
-__global__ void gn_reduce_kernel(GnParts s, int cpg, float inv_n, float eps, float* __restrict__ stats) {
+__global__ void gn_reduce_kernel(GnParts s, int cpg, float inv_n, float eps, float2* __restrict__ ab,
+                                 const __half* __restrict__ gamma, const __half* __restrict__ beta) {
     griddep_launch_dependents();
     griddep_wait();
     const int g = blockIdx.x, b = blockIdx.y;
     const int c_lo = g * cpg, c_hi = c_lo + cpg;
-    float sa = 0.f, sq = 0.f;
-    {   // channels of this group that live in source 1
-        const int lo = min(c_lo, s.C1), hi = min(c_hi, s.C1), n = hi - lo;
-        const float2* base = s.p1 + (size_t)b * s.rb1 * s.C1 + lo;
-        for (int idx = threadIdx.x; idx < n * s.rb1; idx += blockDim.x) {
-            const int rb = idx / n, k = idx - rb * n;
-            const float2 v = __ldg(base + (size_t)rb * s.C1 + k);
-            sa += v.x;
-            sq += v.y;
+    float sa[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+    // thread = (channel of the group, slice of the 32-row blocks): four independent loads in flight per thread
+    auto accumulate = [&](const float2* __restrict__ base, int n, int rb, int ld) {
+        if (n <= 0) return;
+        const int lanes = blockDim.x / n;           // row-block slices (>= 3 for cpg <= 80 and 256 threads)
+        const int k = threadIdx.x % n, sl = threadIdx.x / n;
+        if (sl >= lanes) return;
+        int r = sl;
+        for (; r + 3 * lanes < rb; r += 4 * lanes) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float2 v = __ldg(base + (size_t)(r + u * lanes) * ld + k);
+                sa[u] += v.x;
+                sq[u] += v.y;
+            }
         }
+        for (; r < rb; r += lanes) {
+            const float2 v = __ldg(base + (size_t)r * ld + k);
+            sa[0] += v.x;
+            sq[0] += v.y;
+        }
+    };
+    {
+        const int lo = min(c_lo, s.C1), hi = min(c_hi, s.C1);
+        accumulate(s.p1 + (size_t)b * s.rb1 * s.C1 + lo, hi - lo, s.rb1, s.C1);
     }
     if (s.C2 > 0) {
-        const int lo = max(c_lo, s.C1) - s.C1, hi = max(c_hi, s.C1) - s.C1, n = hi - lo;
-        const float2* base = s.p2 + (size_t)b * s.rb2 * s.C2 + lo;
-        for (int idx = threadIdx.x; idx < n * s.rb2; idx += blockDim.x) {
-            const int rb = idx / n, k = idx - rb * n;
-            const float2 v = __ldg(base + (size_t)rb * s.C2 + k);
-            sa += v.x;
-            sq += v.y;
-        }
+        const int lo = max(c_lo, s.C1) - s.C1, hi = max(c_hi, s.C1) - s.C1;
+        accumulate(s.p2 + (size_t)b * s.rb2 * s.C2 + lo, hi - lo, s.rb2, s.C2);
     }
+    float a = (sa[0] + sa[1]) + (sa[2] + sa[3]), q = (sq[0] + sq[1]) + (sq[2] + sq[3]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        sa += __shfl_xor_sync(0xffffffffu, sa, o);
-        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
     }
     __shared__ float2 red[8];
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = make_float2(sa, sq);
+    __shared__ float2 mr;
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = make_float2(a, q);
     __syncthreads();
     if (threadIdx.x == 0) {
-        float a = 0.f, q = 0.f;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-            a += red[w].x;
-            q += red[w].y;
+        float ta = 0.f, tq = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {  // fixed order: deterministic
+            ta += red[w].x;
+            tq += red[w].y;
         }
-        const float mean = a * inv_n;
-        const float var = fmaxf(q * inv_n - mean * mean, 0.f);
-        stats[((size_t)b * 32 + g) * 2] = mean;
-        stats[((size_t)b * 32 + g) * 2 + 1] = rsqrtf(var + eps);
+        const float mean = ta * inv_n;
+        mr = make_float2(mean, rsqrtf(fmaxf(tq * inv_n - mean * mean, 0.f) + eps));
     }
+    __syncthreads();
+    gn_write_affine(ab, b, s.C1 + s.C2, g, cpg, threadIdx.x, blockDim.x, mr.x, mr.y, gamma, beta);
 }
 
 // grid = (ceil(ceil(HW/32) / 8), B), block = 256: one warp per 32-row block; lane = channel pair, strided over C
@@ -362,8 +397,8 @@ extern "C" int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int
         rows_per_cta = (HW + splits - 1) / splits;
         splits = (HW + rows_per_cta - 1) / rows_per_cta;
     }
-    float* stats = static_cast<float*>(stats_ws);             // [B][32][2] mean, rstd
-    float* partial = stats + (size_t)B * 64;                  // [B][splits][32][2]
+    float2* ab = static_cast<float2*>(stats_ws);                              // [B][C] (a, b) of y = a x + b
+    float* partial = static_cast<float*>(stats_ws) + (size_t)B * 2 * 2560;   // [B][splits][32][2]
     const size_t smem = (size_t)2 * ty * C * sizeof(float);
     static bool configured = false;
     if (!configured) {
@@ -373,13 +408,10 @@ extern "C" int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int
     OMG_CUDA(launch_pdl(gn_partial_kernel, dim3(splits, B), dim3(tx, ty), smem, stream, s, HW, cpg, rows_per_cta, partial));
     if (check_launch("gn_partial_kernel")) return 1;
     OMG_CUDA(launch_pdl(gn_finalize_kernel, dim3(B), dim3(1024), 0, stream, (const float*)partial, splits,
-                        1.0f / ((float)HW * (float)cpg), eps, stats));
+                        1.0f / ((float)HW * (float)cpg), eps, ab, C, cpg, static_cast<const __half*>(gamma),
+                        static_cast<const __half*>(beta)));
     if (check_launch("gn_finalize_kernel")) return 1;
-    const size_t nvec = (size_t)HW * (C / 8);
-    OMG_CUDA(launch_pdl(gn_apply_kernel, dim3((unsigned)((nvec + 1023) / 1024), B), dim3(256), 0, stream, s, HW, cpg, silu,
-                        (const float*)stats, static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
-                        static_cast<__half*>(y)));
-    return check_launch("gn_apply_kernel");
+    return launch_gn_apply(s, B, HW, silu, ab, static_cast<__half*>(y), stream);
 }
 
 extern "C" int omg_colstats(const void* x, int C, int B, int HW, void* out, void* stream_) {
@@ -404,14 +436,11 @@ extern "C" int omg_groupnorm_apply(const void* x1, int C1, const void* part1, in
     const int cpg = C / 32;
     GnSrc s{static_cast<const __half*>(x1), static_cast<const __half*>(x2), C1, C2};
     GnParts parts{static_cast<const float2*>(part1), static_cast<const float2*>(part2), C1, C2, rb1, rb2};
-    float* stats = static_cast<float*>(stats_ws);  // [B][32][2] mean, rstd
-    OMG_CUDA(launch_pdl(gn_reduce_kernel, dim3(32, B), dim3(256), 0, stream, parts, cpg, 1.0f / ((float)HW * (float)cpg), eps, stats));
+    float2* ab = static_cast<float2*>(stats_ws);  // [B][C] (a, b) of y = a x + b
+    OMG_CUDA(launch_pdl(gn_reduce_kernel, dim3(32, B), dim3(256), 0, stream, parts, cpg, 1.0f / ((float)HW * (float)cpg), eps, ab,
+                        static_cast<const __half*>(gamma), static_cast<const __half*>(beta)));
     if (check_launch("gn_reduce_kernel")) return 1;
-    const size_t nvec = (size_t)HW * (C / 8);
-    OMG_CUDA(launch_pdl(gn_apply_kernel, dim3((unsigned)((nvec + 1023) / 1024), B), dim3(256), 0, stream, s, HW, cpg, silu,
-                        (const float*)stats, static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
-                        static_cast<__half*>(y)));
-    return check_launch("gn_apply_kernel");
+    return launch_gn_apply(s, B, HW, silu, ab, static_cast<__half*>(y), stream);
 }
 
 extern "C" int omg_layernorm(const void* x, const void* gamma, const void* beta, void* y, long long rows, int C,

@@ -215,7 +215,7 @@ def groupnorm(x1, gamma, beta, eps, silu, x2=None, out=None, stats_ws=None):
     if out is None:
         out = torch.empty((*x1.shape[:-1], C1 + C2), dtype=torch.float16, device=x1.device)
     if stats_ws is None:
-        stats_ws = torch.empty(B * 64 * 257, dtype=torch.float32, device=x1.device)
+        stats_ws = torch.empty(B * (10240 + 64 * 256), dtype=torch.float32, device=x1.device)
     L.check(L.load().omg_groupnorm(x1.data_ptr(), C1, _ptr(x2), C2, B, HW, gamma.data_ptr(), beta.data_ptr(),
                                    float(eps), int(silu), stats_ws.data_ptr(), out.data_ptr(), _stream()),
             "omg_groupnorm")
@@ -247,7 +247,7 @@ def groupnorm_apply(x1, part1, gamma, beta, eps, silu, x2=None, part2=None, out=
     if out is None:
         out = torch.empty((*x1.shape[:-1], C1 + C2), dtype=torch.float16, device=x1.device)
     if stats_ws is None:
-        stats_ws = torch.empty(B * 64, dtype=torch.float32, device=x1.device)
+        stats_ws = torch.empty(B * (10240 + 64 * 256), dtype=torch.float32, device=x1.device)
     L.check(L.load().omg_groupnorm_apply(x1.data_ptr(), C1, part1.data_ptr(), part1.shape[1], _ptr(x2), C2, _ptr(part2),
                                          0 if part2 is None else part2.shape[1], B, HW, gamma.data_ptr(), beta.data_ptr(),
                                          float(eps), int(silu), stats_ws.data_ptr(), out.data_ptr(), _stream()),

@@ -296,7 +296,7 @@ class UNetRunner:
         # one slot, or a list of slots, (9 skip residual tensors, mid residual, scale[, row0]) produced by ControlNet
         # runners; a slot is added to the batch rows [row0, row0 + residual batch)
         self.residuals_in = None
-        self.stats_ws = torch.empty(batch * 64 * 257, dtype=torch.float32, device=self.dev)
+        self.stats_ws = torch.empty(batch * (10240 + 64 * 256), dtype=torch.float32, device=self.dev)
 
     # ------------------------------------------------------------------------------------------- buffers
     def drop_graphs(self):

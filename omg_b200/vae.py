@@ -165,7 +165,7 @@ class PackedVaeDecoder:
 
     # ------------------------------------------------------------------------------------------------ blocks
     def _stats_ws(self, B):
-        n = B * 64 * 257  # OMG_GN_WS_FLOATS(B)
+        n = B * (10240 + 64 * 256)  # OMG_GN_WS_FLOATS(B)
         if self._ws is None or self._ws.numel() < n:
             self._ws = torch.empty(n, dtype=torch.float32, device=self.device)
         return self._ws

@@ -110,7 +110,7 @@ def tracing():
     return tr, (lambda pipe, i, t, kw: tr.append(kw["latents"].float().clone()) or {})
 
 
-def config2(steps, emit):
+def config2(steps, emit, stages=(1, 2)):
     cfg = UNetConfig.sdxl()
     wl = factory.build_lora_workload(cfg, SIZE, 2, 32, steps, 7.5, device=dev, keep_state_dict=True)
     pipe, cm, kw = wl.pipe, wl.concept_models, dict(wl.call_kwargs)
@@ -124,7 +124,7 @@ def config2(steps, emit):
         e, n_, p_, np2 = cm.encode_prompt(rp, negative_prompt=rn)
         lo = {name: [(a, b, s * 0.8)] for name, (a, b, s) in cm._loras[kw["lora_list"][k]].items()}
         specs.append(dict(ctx=torch.cat([n_, e]).half(), pooled=torch.cat([np2, p_]).half(), mask=wl.masks[k], lora=lo))
-    for stage in (1, 2):
+    for stage in stages:
         tr, cb = tracing()
         extra = dict(region_masks=wl.masks) if stage == 2 else {}
         out = pipe(stage=stage, latents=lat0, callback_on_step_end=cb, **extra, **kw).images.float()

@@ -1,6 +1,6 @@
 """BASELINE config 1 at FULL SDXL widths (2.57 G parameters): one fusion step of stage 2 (step index 16) at 64x64
 latents, main UNet rows (B=4, prompt-to-prompt self-replace window active) + one LoRA concept (B=2) as ONE grouped
-forward, then omg_fuse_step; compared with the fp32 oracle on the host cores.  Tolerances: 5e-3 on the noise
+forward, then omg_fuse_step; compared with the fp32 oracle on the host cores.  Tolerances (1.25 x measured): 2.2e-3 / 2.9e-3 on the noise
 prediction, 3e-3 on the latents after the step (measured: 1.7e-3 / 2.3e-3 / 1.1e-3)."""
 import os
 import time
@@ -115,6 +115,9 @@ def test_config1_full_width_fusion_step():
     out["fp16_eager_rel_err_concept"] = rel(h_c, n_c)
     out["cuda_vs_fp16_eager_main"] = rel(noise_gpu[:4], h_main)
     print(out)
-    assert out["noise_rel_err_main"] < 5e-3 and out["noise_rel_err_concept"] < 5e-3
-    assert out["latent_rel_err_after_step"] < 3e-3
+    assert out["noise_rel_err_main"] < 2.2e-3 and out["noise_rel_err_concept"] < 2.9e-3
+    assert out["latent_rel_err_after_step"] < 1.4e-3
+    # never worse than the reference's own library arithmetic (fp16 eager) against fp32, measured in the same run
+    assert out["noise_rel_err_main"] < out["fp16_eager_rel_err_main"]
+    assert out["noise_rel_err_concept"] < out["fp16_eager_rel_err_concept"]
 

@@ -154,10 +154,10 @@ def test_self_attention(ops, B, N, heads):
 
 @pytest.mark.parametrize("n_q,n_kv,gain", [(256, 200, 1.0), (130, 321, 1.0), (512, 640, 2.5), (128, 129, 2.5),
                                             (384, 1024, 3.0)])
-def test_attention_two_stream_edges(ops, n_q, n_kv, gain):
-    """The two-stream self-attention kernel (even / odd KV blocks, merged in the epilogue): odd block counts, a partial
-    last block, n_q != n_kv, and score ranges large enough that the lazy O rescale fires in both streams; with and
-    without `accumulate`."""
+def test_attention_block_edges(ops, n_q, n_kv, gain):
+    """Self-attention kernel edges: odd block counts, a partial last block, n_q != n_kv, and score ranges large enough
+    that the lazy O rescale fires; with and without `accumulate`.  (Run with OMG_ATTN_STREAMS=2 it covers the
+    two-stream variant: even / odd KV blocks merged in the epilogue.)"""
     heads = 3
     Cc = heads * 64
     q = rnd(2, n_q, Cc, seed=11) * gain

@@ -1,6 +1,7 @@
 """GPU parity of the full two-stage loops (LoRA and InstantID variants) against oracle.pipeline.denoise on the tiny
 topology: 18 steps so that the fusion window (step index > 15) is exercised, P2P self-replace threshold 8x8 tokens,
-two concepts with disjoint masks.  Final-latent tolerance 2e-2 relative (18 chained UNet calls in fp16)."""
+two concepts with disjoint masks.  Final-latent tolerances = 1.3 x the values measured on a B200 (LoRA 2.11e-3, style / None-mask 1.69e-3,
+InstantID 1.00e-3: 18 chained UNet calls at fp16 storage vs the fp32 oracle)."""
 import os
 
 import pytest
@@ -80,7 +81,7 @@ def test_lora_two_stage_pipeline(share, lora_mode, monkeypatch):
     ref2 = denoise(main, lat0.float(), ctx4, pooled4, tid.repeat(4, 1), concepts, 2, STEPS, 7.5)
     e0, e1 = rel(out2[0], ref2[0]), rel(out2[1], ref2[1])
     print("lora pipeline final-latent rel err: layout", e0, "fused", e1)
-    assert e0 < 2e-2 and e1 < 2e-2
+    assert e0 < 2.8e-3 and e1 < 2.8e-3
 
 
 def test_lora_pipeline_skips_concept_without_mask_and_style_adapter():
@@ -116,7 +117,7 @@ def test_lora_pipeline_skips_concept_without_mask_and_style_adapter():
                   tid.repeat(4, 1), concepts, 2, STEPS, 5.0)
     e = rel(out, ref)
     print("style/None-mask pipeline rel err", e)
-    assert e < 2e-2
+    assert e < 2.2e-3
 
 
 @pytest.mark.parametrize("share", [False, True])
@@ -171,7 +172,7 @@ def test_instantid_two_stage_pipeline(share):
                   identity_scale=0.8)
     e = rel(out, ref)
     print("instantid pipeline final-latent rel err", e)
-    assert e < 2e-2
+    assert e < 1.3e-3
 
 
 def test_dedup_mode_reproduces_the_as_executed_result():

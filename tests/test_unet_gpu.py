@@ -1,6 +1,7 @@
 """GPU parity of the UNet / ControlNet executor and of both pipelines against the fp32 CPU oracle, tiny topology
 (same code paths as SDXL: conv tails, GroupNorm over concatenated skips, P2P remaps, LoRA K-segments, IP-adapter,
-ControlNet residuals).  Tolerance: relative L2 <= 5e-3 per UNet call (fp16 activations vs fp32 oracle)."""
+ControlNet residuals).  Tolerance: relative L2 <= 1.9e-3 per UNet call = 1.25 x the largest value measured on a B200 (1.50e-3, general
+P2P two-term step; fp16 storage vs the fp32 oracle fed the same fp16-rounded weights)."""
 import pytest
 import torch
 
@@ -8,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 from util_models import from_nhwc, lora, ocfg, oracle_lora, r16, rel, to_nhwc8, weights  # noqa: E402
 
-TOL = 5e-3
+TOL = 1.9e-3
 
 
 @pytest.fixture(scope="module")
