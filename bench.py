@@ -219,18 +219,34 @@ def _main():
         dist.init_process_group("nccl", device_id=torch.device(dev))
     cfg = UNetConfig.sdxl()
 
-    # weights: generated on rank 0, broadcast once over NCCL (the only collective besides the final gather)
-    t_b0 = time.perf_counter()
-    sd = synthetic.make_state_dict(cfg, seed=0, device=dev, dtype=torch.float16)
+    # weights: generated on rank 0 into ONE flat buffer, a single NCCL broadcast (the only collective besides the final
+    # gather); the other ranks receive straight into their own flat buffer (views = the state dict)
+    from omg_b200 import distributed as omg_dist
+    from omg_b200.config import param_shapes
+    shapes = param_shapes(cfg)
+    t_bcast = 0.0
     if world > 1:
-        for k in sorted(sd):
-            dist.broadcast(sd[k], src=0)
+        if rank == 0:
+            flat, sd = omg_dist.flatten_state_dict(synthetic.make_state_dict(cfg, seed=0, device=dev, dtype=torch.float16))
+        else:
+            flat, sd = omg_dist.empty_flat_state_dict(shapes, dev)
         torch.cuda.synchronize()
-    t_bcast = time.perf_counter() - t_b0
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        omg_dist.broadcast_flat(flat)
+        e1.record()
+        torch.cuda.synchronize()
+        t_bcast = e0.elapsed_time(e1) / 1e3
+    else:
+        sd = synthetic.make_state_dict(cfg, seed=0, device=dev, dtype=torch.float16)
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):  # keep stdout to the single JSON line
         wl = factory.build_lora_workload(cfg, IMAGE, 2, 32, STEPS_PER_STAGE, 7.5, device=dev, state_dict=sd)
     del sd
+    if world > 1:
+        del flat
     pipe = wl.pipe
     kw = dict(wl.call_kwargs)
     prompts, regions = kw["prompt"]

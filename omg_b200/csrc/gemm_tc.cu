@@ -15,6 +15,7 @@
 //
 // Roofline: tensor-bound (ridge ~227 flop/B); algorithmic FLOPs per launch = 2 * pixels * N * sum(k_len).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -80,7 +81,7 @@ struct GemmCfg {
     static constexpr int B_BYTES = (BN / CTAS) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     // per-column epilogue vectors (bias | c1), one plane per sub-tile
-    static constexpr int VEC_PLANE = MT == 2 ? BN : 256;
+    static constexpr int VEC_PLANE = MT == 2 ? BN : (BN > 256 ? BN : 256);
     static constexpr int VEC_BYTES = 2 * MT * VEC_PLANE * 4;
     // tall tiles need the last KB for a 4th stage: they rely on the (in practice guaranteed, checked at run time)
     // 1024 B alignment of the dynamic shared memory window instead of reserving alignment slack
@@ -89,9 +90,11 @@ struct GemmCfg {
     static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = ALIGN_SLACK + STAGES * STAGE_BYTES + STAGING_BYTES + VEC_BYTES + 256;
-    static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator
-    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-    static constexpr int ACC_STAGES = MT == 2 ? 1 : 2;  // MT = 2: the two accumulators ARE the two sub-tiles
+    // BN = 320 (CTA pairs only): a 256 x 320 pair tile = two N = 160 MMAs per K step into one 320-column accumulator
+    // (operand bytes per MMA cycle: 128x256 tiles 96 B/clk, tall 256x160 83, 256x256 pairs 64, 256x320 pairs 56).
+    static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : (BN <= 256 ? 256 : 512));  // TMEM columns per accumulator
+    static constexpr int TMEM_COLS = BN > 256 ? 512 : 2 * ACC_STRIDE;
+    static constexpr int ACC_STAGES = (MT == 2 || BN > 256) ? 1 : 2;  // MT = 2: the two accumulators ARE the two sub-tiles
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -99,6 +102,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 template <int BN, int EPI, int CTAS, int MT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     static_assert(MT == 1 || CTAS == 1, "tall tiles are a single-CTA variant");
+    static_assert(BN <= 256 || (CTAS == 2 && BN == 320 && EPI != OMG_EPI_GEGLU), "BN = 320 exists as a CTA-pair tile only");
     using Cfg = GemmCfg<BN, CTAS, MT>;
     constexpr int MSUB = CTAS * MT;  // 128-row m-tiles per work unit
     constexpr int STAGES = Cfg::STAGES;
@@ -165,7 +169,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 // second 128-row sub-tile of a tall tile (the next m-tile in (w, h, image) order)
                 const int b1 = (m_tile + 1) / tiles_per_img, rem1 = (m_tile + 1) % tiles_per_img;
                 const int h1 = (rem1 / p.tiles_w) * p.th, w1 = (rem1 % p.tiles_w) * p.tw;
-                int n0 = n_tile * BN + (int)cta_rank * (BN / CTAS);  // this CTA's slice of the B tile
+                // this CTA's slice of the B tile (BN = 320: two 80-row slices, one per N = 160 MMA)
+                int n0 = n_tile * BN + (int)cta_rank * (BN > 256 ? 80 : BN / CTAS);
                 if (p.w_group_rows > 0) {  // multi-stream launch: this tile's stream selects the weight plane
                     const long long tile_pix0 = ((long long)b * p.img_h + h0) * p.img_w + w0;
                     for (int g2 = 0; g2 + 1 < p.n_col_groups; ++g2)
@@ -183,6 +188,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                             tma_load_4d_pair(a_dst, &p.a_maps[sg.a_map], &full_bar[stage], sg.a_c0 + kb * BK,
                                              w0 + sg.dx, h0 + sg.dy, b);
                             tma_load_2d_pair(b_dst, &p.b_maps[sg.b_map], &full_bar[stage], sg.b_k0 + kb * BK, n0);
+                            if constexpr (BN > 256)
+                                tma_load_2d_pair(b_dst + 80 * BK * 2, &p.b_maps[sg.b_map], &full_bar[stage], sg.b_k0 + kb * BK,
+                                                 n0 + 160);
                         } else {
                             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                             tma_load_4d(a_dst, &p.a_maps[sg.a_map], &full_bar[stage], sg.a_c0 + kb * BK, w0 + sg.dx,
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     } else if (warp == 1) {
         // ------------------------------------------------------------- MMA issuer (one thread)
         if (lane == 0 && leader) {
-            constexpr uint32_t idesc = umma_idesc_f16(BM * CTAS, BN, false, false);
+            constexpr uint32_t idesc = umma_idesc_f16(BM * CTAS, BN > 256 ? 160 : BN, false, false);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -226,6 +234,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                             // +32 B per K=16 step inside the 128 B swizzle atom (start-address field is >>4)
                             if constexpr (CTAS == 2) tc_mma_f16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate);
                             else tc_mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate);
+                            if constexpr (BN > 256)  // second N = 160 half: the next 80-row slice of B, columns 160..319
+                                tc_mma_f16_ss_pair(d_tmem + 160, a_desc + 2 * k, b_desc + ((80 * BK * 2) >> 4) + 2 * k, idesc,
+                                                   accumulate);
                             if constexpr (MT == 2)  // second sub-tile: A rows 128..255 (+16 KB), accumulator + ACC_STRIDE
                                 tc_mma_f16_ss(d_tmem + Cfg::ACC_STRIDE, a_desc + ((BM * BK * 2) >> 4) + 2 * k, b_desc + 2 * k,
                                               idesc, accumulate);
@@ -495,6 +506,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 if constexpr (MT == 2) {  // this thread covered the whole row of its sub-tile
                     so[(size_t)(n_tile * 2) * p.stats_rows + pix] = make_float2(row_sum, row_sq);
                     so[(size_t)(n_tile * 2 + 1) * p.stats_rows + pix] = make_float2(0.f, 0.f);
+                } else if constexpr (BN > 256) {  // same plane count as two 160-wide tiles (what omg_gemm_plan promised)
+                    so[(size_t)(n_tile * 4 + half) * p.stats_rows + pix] = make_float2(row_sum, row_sq);
+                    so[(size_t)(n_tile * 4 + 2 + half) * p.stats_rows + pix] = make_float2(0.f, 0.f);
                 } else {
                     so[(size_t)(n_tile * 2 + half) * p.stats_rows + pix] = make_float2(row_sum, row_sq);
                 }
@@ -669,7 +683,24 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     int bn = d->block_n ? d->block_n
                         : pick_block_n(d->N, d->epilogue, p.m_tiles, d->row_stats_out ? K_PLAN_LONG : k_blocks_hint,
                                        k_blocks_hint, &prefer_tall);
-    OMG_CHECK(bn == 64 || bn == 128 || bn == 160 || bn == 256, "omg_gemm: block_n=%d unsupported", bn);
+    // block_n = 320 (256 x 320 CTA-pair tiles, two N = 160 MMAs per K step) is available on request and through
+    // OMG_GEMM_320=1 (every 160-wide choice that allows it); never chosen by default: measured equal to the tall 256 x 160
+    // tiles on the linears and 4-7 % slower on the convs (profiles/r02_gemm_tile_ab.jsonl) although it moves a third fewer
+    // operand bytes per MMA cycle - these mainloops are not bound by the L2 -> shared-memory bandwidth.
+    static int allow_320 = -1;
+    if (allow_320 < 0) {
+        const char* e = getenv("OMG_GEMM_320");
+        allow_320 = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    if (allow_320) {
+        bool pair_ok0 = true;
+        for (int i = 0; i + 1 < (d->n_col_groups > 0 ? d->n_col_groups : 1); ++i) pair_ok0 = pair_ok0 && (d->col_group_end[i] % 256 == 0);
+        if (!d->block_n && d->cta_pair == 0 && bn == 160 && !geglu && d->N % 320 == 0 && pair_ok0 && p.m_tiles >= 2 &&
+            k_blocks_hint >= 8)
+            bn = 320;
+    }
+    OMG_CHECK(bn == 64 || bn == 128 || bn == 160 || bn == 256 || bn == 320, "omg_gemm: block_n=%d unsupported", bn);
+    OMG_CHECK(bn != 320 || (!geglu && d->N % 320 == 0), "omg_gemm: block_n=320 needs N %% 320 == 0 and no GEGLU");
     if (geglu) bn = 256;
     p.n_tiles = (d->N + bn - 1) / bn;
     p.bias = static_cast<const __half*>(d->bias);
@@ -716,7 +747,7 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
         const uint64_t planes = d->w_group_planes > 0 ? (uint64_t)d->w_group_planes : 1;
         const uint64_t dims[2] = {(uint64_t)d->Ktot, (uint64_t)d->N * planes};
         const uint64_t strides[2] = {1, (uint64_t)d->Ktot};
-        const uint32_t box[2] = {BK, (uint32_t)bn};
+        const uint32_t box[2] = {BK, (uint32_t)std::min(bn, 256)};
         if (make_tmap_f16(&p.b_maps[0], d->w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
         p.b_maps[1] = p.b_maps[0];
     }
@@ -724,7 +755,7 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
         OMG_CHECK(d->K2tot >= 8 && d->K2tot % 8 == 0, "omg_gemm: K2tot=%d must be a positive multiple of 8", d->K2tot);
         const uint64_t dims[2] = {(uint64_t)d->K2tot, (uint64_t)d->N};
         const uint64_t strides[2] = {1, (uint64_t)d->K2tot};
-        const uint32_t box[2] = {BK, (uint32_t)bn};
+        const uint32_t box[2] = {BK, (uint32_t)std::min(bn, 256)};
         if (make_tmap_f16(&p.b_maps[1], d->w2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     }
     if (view_to_tmap(&p.d_map, d->d, 32, p.store_w, p.store_h, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
@@ -752,8 +783,10 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     bool pair_ok = true;  // both CTAs of a pair must belong to the same stream
     for (int i = 0; i + 1 < p.n_col_groups; ++i) pair_ok = pair_ok && (p.col_group_end[i] % 256 == 0);
     // BN = 160 pairs are available on request but never chosen: measured 0..-8 % (profiles/r01_kernel_bench.json)
-    const bool pair = (bn == 256 || (bn == 160 && !geglu)) && pair_ok &&
-                      (d->cta_pair == 2 || (d->cta_pair == 0 && bn == 256 && use_cta_pair(p.m_tiles, p.n_tiles, k_blocks)));
+    OMG_CHECK(bn != 320 || (pair_ok && p.m_tiles >= 2 && d->cta_pair != 1 && d->cta_pair != 3),
+              "omg_gemm: block_n=320 runs as CTA pairs only (>= 2 m-tiles, 256-row aligned stream boundaries)");
+    const bool pair = bn == 320 || ((bn == 256 || (bn == 160 && !geglu)) && pair_ok &&
+                      (d->cta_pair == 2 || (d->cta_pair == 0 && bn == 256 && use_cta_pair(p.m_tiles, p.n_tiles, k_blocks))));
     if (pair) {
         for (int i = 0; i < 2; ++i) {
             const void* wp = i == 0 ? d->w : d->w2;
@@ -762,11 +795,12 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
             const uint64_t planes = (i == 0 && d->w_group_planes > 0) ? (uint64_t)d->w_group_planes : 1;
             const uint64_t dims[2] = {(uint64_t)kt, (uint64_t)d->N * planes};
             const uint64_t strides[2] = {1, (uint64_t)kt};
-            const uint32_t box[2] = {BK, (uint32_t)(bn / 2)};
+            const uint32_t box[2] = {BK, (uint32_t)(bn == 320 ? 80 : bn / 2)};
             if (make_tmap_f16(&p.b_maps[i], wp, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
         }
         if (!d->w2) p.b_maps[1] = p.b_maps[0];
         if (geglu) return launch_gemm<256, OMG_EPI_GEGLU, 2>(p, stream);
+        if (bn == 320) return launch_gemm<320, OMG_EPI_NONE, 2>(p, stream);
         if (bn == 160) return launch_gemm<160, OMG_EPI_NONE, 2>(p, stream);
         return launch_gemm<256, OMG_EPI_NONE, 2>(p, stream);
     }

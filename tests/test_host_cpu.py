@@ -138,6 +138,19 @@ def _dp_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sd = {"b": torch.full((3,), float(rank)), "a": torch.arange(4.0) * (rank + 1)}
     broadcast_state_dict(sd, 0)
+    # the form bench.py uses: rank 0 packs its weights into ONE flat buffer, the others receive into an empty one
+    from omg_b200.distributed import broadcast_flat, empty_flat_state_dict, flat_layout, flatten_state_dict
+    shapes = {"w": (5, 3), "v": (7,), "u": (2, 2, 2)}
+    if rank == 0:
+        src = {k: torch.arange(float(torch.tensor(shp).prod())).reshape(shp) + i for i, (k, shp) in enumerate(shapes.items())}
+        flat, views = flatten_state_dict(src, dtype=torch.float32)
+    else:
+        flat, views = empty_flat_state_dict(shapes, "cpu", dtype=torch.float32)
+    broadcast_flat(flat, 0)
+    layout, total = flat_layout(shapes)
+    assert flat.numel() == total and all(off % 128 == 0 for off, _ in layout.values())
+    for i, (k, shp) in enumerate(shapes.items()):
+        assert torch.equal(views[k], torch.arange(float(torch.tensor(shp).prod())).reshape(shp) + i)
     n = 5
     idx = shard_indices(n, rank, world)
     local = torch.stack([torch.full((2, 2), float(j)) for j in idx])

@@ -28,7 +28,9 @@ def ops():
 
 @pytest.mark.parametrize("M,N,K,bn", [(256, 256, 128, 0), (4096, 1280, 1280, 0), (1000, 640, 320, 0),
                                       (308, 2560, 2048, 0), (4, 1280, 2816, 0), (512, 320, 960, 160),
-                                      (512, 320, 960, 64), (2048, 1920, 640, 128), (2048, 1280, 640, 256)])
+                                      (512, 320, 960, 64), (2048, 1920, 640, 128), (2048, 1280, 640, 256),
+                                      (4096, 1280, 1280, 320), (512, 640, 1024, 320), (300, 320, 640, 320),
+                                      (2176, 960, 192, 320)])
 def test_linear(ops, M, N, K, bn):
     x, w, b = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2), rnd(N, seed=3)
     r = rnd(M, N, seed=4)
@@ -478,3 +480,34 @@ def test_column_statistics_of_down_and_up_convs(ops):
     ops.upsample2x_conv3x3(x, wd, bias=rnd(C, seed=4), out=u, colstats=pu)
     assert torch.allclose(pu.sum(1)[..., 0], u.float().sum((1, 2)), rtol=1e-3, atol=5e-2)
     assert torch.allclose(pu.sum(1)[..., 1], (u.float() ** 2).sum((1, 2)), rtol=1e-3, atol=5e-2)
+
+
+def test_pair320_tiles_conv_residual_stats_and_lora(ops):
+    """256 x 320 CTA-pair tiles (two N = 160 MMAs per K step, one 320-column accumulator): a conv with time-embedding
+    row vector and residual, GroupNorm column statistics and LayerNorm row statistics out of the same epilogue, an
+    un-merged LoRA K-segment against the second weight matrix."""
+    from omg_b200 import _lib as L
+    B, H, W, Cin, N = 3, 16, 16, 128, 640
+    x = rnd(B, H, W, Cin, seed=1)
+    w = rnd(N, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    bias, temb, res = rnd(N, seed=3), rnd(B, N, seed=4), rnd(B, H, W, N, seed=5)
+    part = torch.full((B, ops.colstats_blocks(W, H), N, 2), float("nan"), device="cuda")
+    out = ops.conv3x3(x, ops.pack_conv3x3_weight(w), bias=bias, rowvec=temb, residual=res, block_n=320, colstats=part)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias.float(), padding=1) + temb.float()[:, :, None, None] \
+        + res.float().permute(0, 3, 1, 2)
+    assert rel(out.permute(0, 3, 1, 2), ref) < 2e-3
+    assert torch.allclose(part.sum(1)[..., 0], out.float().sum((1, 2)), rtol=1e-3, atol=5e-2)
+    # row statistics (LayerNorm fold producer) + LoRA segment, default tile choice (auto-upgraded from 160 to 320)
+    M, C = 1024, 640
+    o, wo = rnd(M, C, seed=6), rnd(C, C, scale=C ** -0.5, seed=7)
+    t, b2 = rnd(M, 32, seed=8), rnd(C, 32, scale=0.1, seed=9)
+    h0 = rnd(M, C, seed=10)
+    parts = ops.gemm_plan(C, L.EPI_NONE, M)[1]
+    stats = torch.full((parts, M, 2), float("nan"), device="cuda")
+    h = h0.clone()
+    ops.linear(o, wo, residual=h, out=h, stats_out=stats, lora=(t, b2))
+    href = o.float() @ wo.float().t() + t.float() @ b2.float().t() + h0.float()
+    assert rel(h, href) < 2e-3
+    sm = stats.sum(0)
+    assert torch.allclose(sm[:, 0], href.sum(1), rtol=2e-3, atol=3e-2)
+    assert torch.allclose(sm[:, 1], (href * href).sum(1), rtol=3e-3, atol=3e-2)
