@@ -159,8 +159,10 @@ def run_reference(args, rank, world):
     })
 
 
-def workload_config(n_gpus):
-    return {"workload": "BASELINE config 2: SDXL UNet (random-init, 2.57 G params), 1024x1024 (latent 128x128), two-stage "
+def workload_config(n_gpus, total_images=0):
+    cfg5 = (f"BASELINE config 5: {total_images} independent images (seeds 0..{total_images - 1}) sharded image j -> rank j mod "
+            f"{n_gpus}; each image = " if total_images else "")
+    return {"workload": cfg5 + "BASELINE config 2: SDXL UNet (random-init, 2.57 G params), 1024x1024 (latent 128x128), two-stage "
                         "OMG loop, 30 steps per stage, 2 LoRA concepts (rank 32 on every transformer Linear), guidance "
                         "7.5, prompt-to-prompt AttentionReplace(50, cross 1.0, self 0.4), as-executed 296 UNet "
                         "sample-forwards per image",
@@ -198,6 +200,9 @@ def _main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--total-images", type=int, default=0,
+                    help="BASELINE config 5: this many independent images (seeds 0..N-1) sharded image j -> rank j mod G "
+                         "(strong scaling); overrides --steps")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -287,11 +292,17 @@ def _main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    seeds = [14 + rank * 1000 + i for i in range(args.steps)]
+    if args.total_images:
+        from omg_b200.distributed import shard_indices
+        seeds = shard_indices(args.total_images, rank, world)   # seeds 0..N-1
+        args.steps = len(seeds)
+
     def timed(k, src, to_host):
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        outs = [one_image(14 + rank * 1000 + i, src, to_host) for i in range(k)]
+        outs = [one_image(seeds[i], src, to_host) for i in range(k)]
         e1.record()
         sync_all()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -318,7 +329,7 @@ def _main():
     finite = all(bool(torch.isfinite(o[1]).all()) for o in outs)
 
     if rank == 0:
-        imgs = args.steps * world
+        imgs = args.total_images if args.total_images else args.steps * world
         value = imgs / (ms / 1e3)
         e2e = imgs / (ms_e2e / 1e3)
         peaks = read_peaks()
@@ -363,8 +374,8 @@ def _main():
         out = {
             "metric": "1024^2 images/sec @30 steps, 2 concepts", "value": value, "unit": "images/sec",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": workload_config(world),
+            "higher_is_better": True, "scaling": "strong" if args.total_images else "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic", "config": workload_config(world, args.total_images),
             "e2e": {"value": e2e, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

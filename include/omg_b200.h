@@ -37,7 +37,7 @@ typedef struct {
     int32_t b_idx; /* 0: columns of w, 1: columns of w2 (e.g. the LoRA up-projection B, kept un-merged) */
 } omg_seg;
 
-enum { OMG_EPI_NONE = 0, OMG_EPI_GEGLU = 1, OMG_EPI_SILU = 2 };
+enum { OMG_EPI_NONE = 0, OMG_EPI_GEGLU = 1, OMG_EPI_SILU = 2, OMG_EPI_QUICK_GELU = 3, OMG_EPI_GELU = 4 };
 
 /*
  * out[pix, n] = epi( sum_seg sum_k A_seg[pix+(dx,dy), k] * W[n, b_k0+k] + bias[n] + rowvec[b, n] ) + residual[pix, n]
@@ -47,6 +47,8 @@ enum { OMG_EPI_NONE = 0, OMG_EPI_GEGLU = 1, OMG_EPI_SILU = 2 };
  * (cuBLAS / cuDNN in the reference).  tcgen05 tensor cores, TMA-staged operands.
  * OMG_EPI_GEGLU: W rows (and bias) are interleaved (value_j, gate_j) pairs; out has N/2 channels,
  * out_j = value_j * gelu_erf(gate_j).   OMG_EPI_SILU: epi(x) = x * sigmoid(x) (time-embedding MLPs).
+ * OMG_EPI_QUICK_GELU: x * sigmoid(1.702 x), OMG_EPI_GELU: erf-gelu (the fc1 activations of the two CLIP text towers,
+ * transformers CLIPMLP [3P], reached from src/pipelines/lora_pipeline.py:315-347).
  */
 typedef struct {
     omg_view4 a[OMG_MAX_A];
@@ -131,6 +133,7 @@ typedef struct {
     float scale;      /* softmax scale, head_dim^-0.5 */
     float out_weight; /* weight of this term */
     int32_t accumulate;
+    int32_t causal;   /* 1: key j attends only to queries i >= j (CLIP text towers); n_kv <= 128 only */
 } omg_attn_desc;
 
 int omg_attention(const omg_attn_desc* desc, void* stream);

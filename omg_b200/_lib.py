@@ -10,7 +10,7 @@ OMG_MAX_A = 4
 OMG_MAX_SEGS = 12
 OMG_ATTN_MAX_ITEMS = 16
 OMG_MAX_CONCEPTS = 8
-EPI_NONE, EPI_GEGLU, EPI_SILU = 0, 1, 2
+EPI_NONE, EPI_GEGLU, EPI_SILU, EPI_QUICK_GELU, EPI_GELU = 0, 1, 2, 3, 4
 
 
 class View4(C.Structure):
@@ -44,7 +44,7 @@ class AttnDesc(C.Structure):
                 ("n_items", C.c_int32),
                 ("out_b", C.c_int32 * OMG_ATTN_MAX_ITEMS), ("q_b", C.c_int32 * OMG_ATTN_MAX_ITEMS),
                 ("k_b", C.c_int32 * OMG_ATTN_MAX_ITEMS), ("v_b", C.c_int32 * OMG_ATTN_MAX_ITEMS),
-                ("scale", C.c_float), ("out_weight", C.c_float), ("accumulate", C.c_int32)]
+                ("scale", C.c_float), ("out_weight", C.c_float), ("accumulate", C.c_int32), ("causal", C.c_int32)]
 
 
 class FuseDesc(C.Structure):

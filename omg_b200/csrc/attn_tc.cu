@@ -71,6 +71,7 @@ struct alignas(64) AttnParams {
     float scale_log2;  // softmax scale * log2(e)
     float out_weight;
     int accumulate;
+    int causal;  // cross kernel only: key index > query index is masked
 };
 
 // Pipeline (per 128-row tile g, KV block j, buffer b = j & 1):
@@ -764,7 +765,7 @@ __global__ void __launch_bounds__(256, 2) attn_cross_kernel(const __grid_constan
 #pragma unroll
                 for (int t = 0; t < 32; ++t)
                     if (c * 32 + t < NK) {
-                        if (c * 32 + t >= p.n_kv) sr[c][t] = __float_as_uint(-INFINITY);
+                        if (c * 32 + t >= p.n_kv || (p.causal && c * 32 + t > qrow)) sr[c][t] = __float_as_uint(-INFINITY);
                         mx = fmaxf(mx, __uint_as_float(sr[c][t]));
                     }
             const float m = mx * p.scale_log2;
@@ -952,12 +953,14 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
     p.scale_log2 = d->scale * 1.4426950408889634f;
     p.out_weight = d->out_weight;
     p.accumulate = d->accumulate;
+    p.causal = d->causal;
+    OMG_CHECK(!d->causal || (d->n_kv <= 128 && d->n_q <= 128), "omg_attention: causal masking is available for sequences of <= 128 tokens");
     // Single-tile CTAs, two per SM, for every shape: two independent CTAs overlap each other's prologue / epilogue
     // with the other's main loop, which the two-tile CTA (tiles start and end together) cannot (measured, 5 KV
     // stages each: 604 vs 569 TFLOP/s at N = 4096, 388 vs 362 at N = 1024).  Short key sequences (cross-attention,
     // one or two KV blocks) take the 3-stage variant: less shared memory to set up per CTA.
     const int tiles = force_g ? force_g : 1;
-    if (!force_g && cross_kernel && d->n_kv <= 128) {
+    if ((!force_g && cross_kernel && d->n_kv <= 128) || d->causal) {
         if (d->n_kv <= 16) return launch_cross<16>(p, d, stream, max_qb, max_kb, max_vb);
         if (d->n_kv <= 80) return launch_cross<80>(p, d, stream, max_qb, max_kb, max_vb);
         return launch_cross<128>(p, d, stream, max_qb, max_kb, max_vb);

@@ -406,9 +406,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sb[j];
                     }
-                    if (p.act_silu) {
+                    if (p.act_silu == 1) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
+                    } else if (p.act_silu == 2) {  // quick_gelu
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-1.702f * v[j]));
+                    } else if (p.act_silu == 3) {  // erf-gelu
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                     }
                     if (has_res) {
 #pragma unroll
@@ -651,7 +657,8 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     OMG_CHECK(d->Ktot % 8 == 0, "omg_gemm: Ktot=%d must be a multiple of 8", d->Ktot);
     const bool geglu = d->epilogue == OMG_EPI_GEGLU;
     const bool silu = d->epilogue == OMG_EPI_SILU;
-    OMG_CHECK(d->epilogue == OMG_EPI_NONE || geglu || silu, "omg_gemm: unknown epilogue %d", d->epilogue);
+    const int act = silu ? 1 : (d->epilogue == OMG_EPI_QUICK_GELU ? 2 : (d->epilogue == OMG_EPI_GELU ? 3 : 0));
+    OMG_CHECK(d->epilogue == OMG_EPI_NONE || geglu || act, "omg_gemm: unknown epilogue %d", d->epilogue);
     const int N_out = geglu ? d->N / 2 : d->N;
     OMG_CHECK(d->d.C == N_out, "omg_gemm: output view has %d channels, expected %d", d->d.C, N_out);
     OMG_CHECK(!geglu || (d->N % 64 == 0 && !d->residual && !d->rowvec),
@@ -708,7 +715,7 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     p.rowvec_ld = d->rowvec_ld;
     p.residual = static_cast<const __half*>(d->residual);
     p.residual_ld = d->residual_ld;
-    p.act_silu = silu ? 1 : 0;
+    p.act_silu = act;  // 0 none, 1 SiLU, 2 quick_gelu, 3 erf-gelu
     p.stats_out = static_cast<float*>(d->row_stats_out);
     p.stats_in = static_cast<const float*>(d->row_stats_in);
     p.stats_parts = d->row_stats_parts;

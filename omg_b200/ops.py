@@ -185,7 +185,7 @@ def upsample2x_conv3x3(x, w, bias=None, out=None, block_n=0, colstats=None):
 
 
 def attention(q, k, v, out, heads, n_q, n_kv, items, q_col0=0, k_col0=0, v_col0=0, out_col0=0, scale=0.125,
-              out_weight=1.0, accumulate=False):
+              out_weight=1.0, accumulate=False, causal=False):
     """q/k/v/out: [batch, tokens, ld] fp16.  items: list of (out_b, q_b, k_b, v_b)."""
     for t in (q, k, v, out):
         _chk16(t)
@@ -199,7 +199,7 @@ def attention(q, k, v, out, heads, n_q, n_kv, items, q_col0=0, k_col0=0, v_col0=
     d.n_items = len(items)
     for i, (ob, qb, kb, vb) in enumerate(items):
         d.out_b[i], d.q_b[i], d.k_b[i], d.v_b[i] = ob, qb, kb, vb
-    d.scale, d.out_weight, d.accumulate = scale, out_weight, int(accumulate)
+    d.scale, d.out_weight, d.accumulate, d.causal = scale, out_weight, int(accumulate), int(causal)
     L.check(L.load().omg_attention(C.byref(d), _stream()), "omg_attention")
     return out
 
