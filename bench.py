@@ -200,6 +200,7 @@ def _main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profile runs only: do not repeat the timed region with host buffers")
     ap.add_argument("--total-images", type=int, default=0,
                     help="BASELINE config 5: this many independent images (seeds 0..N-1) sharded image j -> rank j mod G "
                          "(strong scaling); overrides --steps")
@@ -321,7 +322,7 @@ def _main():
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt.item())
     clocks = sampler.stop() if sampler else None
-    ms_e2e, outs_h = timed(args.steps, host, True)
+    ms_e2e, outs_h = (float("nan"), None) if args.skip_e2e else timed(args.steps, host, True)
     if world > 1:  # gather final latents (128 KiB per image) on every rank
         mine = torch.stack([o[1] for o in outs]).to(dev)
         gathered = [torch.empty_like(mine) for _ in range(world)]
@@ -401,7 +402,7 @@ def _main():
             e1.record()
             torch.cuda.synchronize()
             out["unet_step_ms"]["main_b4"] = e0.elapsed_time(e1) / 5
-        if world == 1:
+        if world == 1 and not args.total_images:
             # "effective" throughput with the opt-in exact de-duplication (twin rows + stage-2 prefix,
             # 172 instead of 296 UNet sample-forwards per image, same latents); reported separately, never as `value`
             wl.pipe.dedup = True

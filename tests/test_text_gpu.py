@@ -51,12 +51,12 @@ def test_clip_towers_on_the_kernels_match_transformers():
     assert p1 is None and p2.shape == (2, 256)
     errs = (rel(h1, r1.hidden_states[-2]), rel(h2, r2.hidden_states[-2]), rel(p2, r2.text_embeds))
     print("clip towers rel err: penultimate L", errs[0], "penultimate bigG-style", errs[1], "text_embeds", errs[2])
-    assert max(errs) < 3e-3
+    assert max(errs) < 1e-3   # measured 6.0e-4 / 6.6e-4 / 7.7e-4
     # the prompt encoder the pipelines use routes through the kernels on CUDA and keeps encode_prompt's layout
     import copy
     enc = ClipPromptEncoder([tok, tok], [copy.deepcopy(e1), copy.deepcopy(e2)], device="cuda", dtype=torch.float16)
     assert enc.use_kernels
     emb, pooled = enc("a man and a woman on the beach")
     assert emb.shape == (77, 192 + 320) and pooled.shape == (256,)
-    assert rel(emb, torch.cat([r1.hidden_states[-2][0], r2.hidden_states[-2][0]], -1)) < 3e-3
-    assert rel(pooled, r2.text_embeds[0]) < 3e-3
+    assert rel(emb, torch.cat([r1.hidden_states[-2][0], r2.hidden_states[-2][0]], -1)) < 1e-3
+    assert rel(pooled, r2.text_embeds[0]) < 1e-3
