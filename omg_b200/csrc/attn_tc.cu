@@ -23,6 +23,8 @@
 // exp2 runs on the MUFU for 11 of 16 element pairs and as a degree-3 polynomial on the FMA pipe for the other 5
 // (MUFU only: 529 TFLOP/s; ncu in profiles/r01_ncu_full_summary.csv).
 #include <cuda_fp16.h>
+
+#include <algorithm>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -344,6 +346,299 @@ __global__ void __launch_bounds__(AttCfg<G, KVS>::THREADS, G == 1 ? 2 : 1) attn_
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent form of the single-stream kernel.  A CTA of the per-tile kernel costs ~6 us of setup and drain (CTA launch,
+// barrier init, TMEM allocation, first Q/K/V round trip, pipeline ramp, epilogue, dealloc) - a third of an N = 1024
+// tile (16 KV blocks x ~0.75 us) - measured as the intercept of round time over KV blocks between N = 4096 and N = 1024.
+// Here 2 x #SM CTAs each walk tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...  as ONE stream of KV blocks: barriers
+// and TMEM live for the whole kernel, the TMA warp runs ahead into the next tile (Q is double-buffered), the MMA issuer
+// starts the next tile's Q.K^T while the softmax group is still in the current tile's epilogue, and only the first
+// P.V of a tile waits for the softmax group to have read the previous tile's O out of tensor memory (o_free).
+// Barrier phases are tracked with running counters, so tiles with odd block counts need no special case.
+template <int KVS_, int QB_>
+struct AttPCfg {
+    static constexpr int THREADS = 256;
+    static constexpr int KV_STAGES = KVS_;
+    static constexpr int Q_BUFS = QB_;
+    // no alignment slack: two CTAs per SM leave 115 712 B each; the dynamic window is 1024 B aligned in practice (checked)
+    static constexpr int SMEM = Q_BUFS * ATT_Q_BYTES + KV_STAGES * 2 * ATT_K_BYTES + 512;
+    static constexpr int TMEM_COLS = 256;
+    static constexpr int O_COL0 = 128, P_COL0 = 192;
+};
+
+template <int KVS_, int QB>
+__global__ void __launch_bounds__(256, 2) attn_p_kernel(const __grid_constant__ AttnParams p, int n_tiles, int n_slabs) {
+    using Cfg = AttPCfg<KVS_, QB>;
+    constexpr int KVS = Cfg::KV_STAGES;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem) & 1023u) != 0) __trap();  // the swizzled tiles need 1024 B alignment
+    uint8_t* q_smem = smem;                                   // 2 x 16 KB
+    uint8_t* kv_smem = q_smem + QB * ATT_Q_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + KVS * 2 * ATT_K_BYTES);
+    uint64_t* q_full = bars;                 // [2]
+    uint64_t* q_empty = bars + 2;            // [2] every Q.K^T of the tile that used the buffer has completed
+    uint64_t* kv_full = bars + 4;            // [KVS]
+    uint64_t* kv_empty = kv_full + KVS;      // [KVS]
+    uint64_t* s_full = kv_empty + KVS;       // [2]
+    uint64_t* p_full = s_full + 2;           // [2]
+    uint64_t* p_empty = p_full + 2;          // [2]
+    uint64_t* o_free = p_empty + 2;          // the softmax group has read the finished tile's O out of TMEM
+    uint64_t* o_done = o_free + 1;           // the last P.V of a tile has completed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nkv = (p.n_kv + ATT_BKV - 1) / ATT_BKV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.q_map);
+        tma_prefetch_desc(&p.k_map);
+        tma_prefetch_desc(&p.v_map);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&q_empty[i], 1);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], 4);
+            mbar_init(&p_empty[i], 1);
+        }
+        for (int i = 0; i < KVS; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        mbar_init(o_free, 4);
+        mbar_init(o_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();
+    griddep_wait();
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == 0) {
+            if (lane == 0) {  // ------------------------------------------------------------ TMA producer
+                uint32_t gj = 0;  // running KV-block counter of this CTA
+                int ti = 0;       // running tile counter
+                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+                    const int slab = tile % n_slabs, head = (tile / n_slabs) % p.heads, item = tile / (n_slabs * p.heads);
+                    const int qb = ti % QB;
+                    mbar_wait(&q_empty[qb], ((ti / QB) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&q_full[qb], ATT_Q_BYTES);
+                    tma_load_3d(q_smem + qb * ATT_Q_BYTES, &p.q_map, &q_full[qb], p.q_col0 + head * ATT_D, slab * ATT_BQ, p.q_b[item]);
+                    const int kb = p.k_b[item], vb = p.v_b[item];
+                    for (int j = 0; j < nkv; ++j, ++gj) {
+                        const int stage = gj % KVS;  // KVS is a compile-time constant
+                        mbar_wait(&kv_empty[stage], ((gj / KVS) & 1) ^ 1);
+                        uint8_t* kd = kv_smem + stage * 2 * ATT_K_BYTES;
+                        mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_K_BYTES);
+                        tma_load_3d(kd, &p.k_map, &kv_full[stage], p.k_col0 + head * ATT_D, j * ATT_BKV, kb);
+                        tma_load_3d(kd + ATT_K_BYTES, &p.v_map, &kv_full[stage], p.v_col0 + head * ATT_D, j * ATT_BKV, vb);
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {  // ------------------------------------------------------------ MMA issuer
+                constexpr uint32_t idesc_s = umma_idesc_f16(128, ATT_BKV, false, false);
+                constexpr uint32_t idesc_o = umma_idesc_f16(128, ATT_D, false, true);
+                const uint64_t k_desc0 = umma_desc_sw128(smem_u32(kv_smem), 1024, 16);
+                const uint64_t v_desc0 = umma_desc_sw128(smem_u32(kv_smem + ATT_K_BYTES), 1024, 1024);
+                // every tile contributes nkv blocks to ONE running sequence g = ti * nkv + j; S / P buffers alternate with g
+                int n_my = 0;
+                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ++n_my;
+                const uint32_t total = (uint32_t)n_my * (uint32_t)nkv;
+                uint32_t sg = 0;       // running block the next Q.K^T belongs to, and its (tile, block) coordinates
+                int s_ti = 0, s_j = 0;
+                auto issue_s = [&]() {  // scores of running block sg into S[sg & 1]
+                    const int qb = s_ti % QB;
+                    if (s_j == 0) {
+                        mbar_wait(&q_full[qb], (s_ti / QB) & 1);
+                        tc_fence_after();
+                    }
+                    const uint32_t st = sg % KVS;
+                    mbar_wait(&kv_full[st], (sg / KVS) & 1);
+                    tc_fence_after();
+                    const uint64_t q_desc = umma_desc_sw128(smem_u32(q_smem + qb * ATT_Q_BYTES), 1024, 16);
+                    const uint64_t kd = k_desc0 + (uint64_t)(st * ((2 * ATT_K_BYTES) >> 4));
+#pragma unroll
+                    for (int k = 0; k < ATT_D / 16; ++k)
+                        tc_mma_f16_ss(tmem_base + (sg & 1) * 64, q_desc + 2 * k, kd + 2 * k, idesc_s, k > 0);
+                    tc_commit(&s_full[sg & 1]);
+                    if (s_j == nkv - 1) tc_commit(&q_empty[qb]);  // last Q.K^T of the tile: its Q buffer may be refilled
+                    ++sg;
+                    if (++s_j == nkv) {
+                        s_j = 0;
+                        ++s_ti;
+                    }
+                };
+                for (uint32_t g = 0; g < 2 && g < total; ++g) issue_s();
+                int ti = 0, j = 0;
+                for (uint32_t g = 0; g < total; ++g) {
+                    const int b = g & 1;
+                    mbar_wait(&p_full[b], (g >> 1) & 1);
+                    tc_fence_after();
+                    if (sg < total) issue_s();
+                    if (j == 0 && ti > 0) {  // O still holds the previous tile until the softmax group has read it
+                        mbar_wait(o_free, (ti - 1) & 1);
+                        tc_fence_after();
+                    }
+                    const uint64_t vd = v_desc0 + (uint64_t)((g % KVS) * ((2 * ATT_K_BYTES) >> 4));
+#pragma unroll
+                    for (int k = 0; k < ATT_BKV / 16; ++k)
+                        tc_mma_f16_ts(tmem_base + Cfg::O_COL0, tmem_base + Cfg::P_COL0 + b * 32 + 8 * k, vd + 128 * k, idesc_o,
+                                      (j > 0 || k > 0) ? 1u : 0u);
+                    tc_commit(&p_empty[b]);
+                    tc_commit(&kv_empty[g % KVS]);
+                    if (j == nkv - 1) tc_commit(o_done);
+                    if (++j == nkv) {
+                        j = 0;
+                        ++ti;
+                    }
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------------------------- softmax group
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t s_tmem = tmem_base + lane_base;
+        const uint32_t o_tmem = tmem_base + Cfg::O_COL0 + lane_base;
+        const uint32_t p_tmem = tmem_base + Cfg::P_COL0 + lane_base;
+        constexpr float kRescaleThreshold = 8.0f;
+        const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2);
+        uint32_t g = 0;
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+            const int slab = tile % n_slabs, head = (tile / n_slabs) % p.heads, item = tile / (n_slabs * p.heads);
+            float m = -INFINITY, l = 0.f;
+            for (int j = 0; j < nkv; ++j, ++g) {
+                const int b = g & 1;
+                mbar_wait(&s_full[b], (g >> 1) & 1);
+                tc_fence_after();
+                const int kv_left = p.n_kv - j * ATT_BKV;
+                uint32_t sr[2][32];
+                tmem_ld_32x32(s_tmem + b * 64, sr[0]);
+                tmem_ld_32x32(s_tmem + b * 64 + 32, sr[1]);
+                tc_wait_ld();
+                if (kv_left < ATT_BKV) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i >= kv_left) sr[c][i] = __float_as_uint(-INFINITY);
+                }
+                float mx = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
+                const float m_cand = fmaxf(m, mx * p.scale_log2);
+                if (j == 0) {
+                    m = m_cand;
+                } else {
+                    const bool need = (m_cand - m) > kRescaleThreshold;
+                    if (__any_sync(0xffffffffu, need)) {
+                        // P.V of the previous block (same tile: j >= 1) must have landed before O is rescaled
+                        mbar_wait(&p_empty[b ^ 1], ((g - 1) >> 1) & 1);
+                        tc_fence_after();
+                        const float corr = need ? fast_exp2(m - m_cand) : 1.0f;
+                        if (need) m = m_cand;
+                        l *= corr;
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t r[32];
+                            tmem_ld_32x32(o_tmem + c * 32, r);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+                            tmem_st_32x32(o_tmem + c * 32, r);
+                        }
+                        tc_wait_st();
+                    }
+                }
+                if (g >= 2) mbar_wait(&p_empty[b], ((g >> 1) & 1) ^ 1);  // P[b] consumed by the P.V of running block g - 2
+                uint64_t sum2 = pack_f32x2(0.f, 0.f);
+                const uint64_t negm2 = pack_f32x2(-m, -m);
+                uint32_t pk[32];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint64_t x2 = ffma2(pack_f32x2(__uint_as_float(sr[c][2 * i]), __uint_as_float(sr[c][2 * i + 1])),
+                                                  scale2, negm2);
+                        float x0, x1, p0, p1;
+                        unpack_f32x2(x2, x0, x1);
+                        if ((OMG_ATT_POLY_MASK >> i) & 1) {
+                            poly_exp2_x2(x0, x1, p0, p1);
+                        } else {
+                            p0 = fast_exp2(x0);
+                            p1 = fast_exp2(x1);
+                        }
+                        sum2 = fadd2(sum2, pack_f32x2(p0, p1));
+                        pk[c * 16 + i] = pack_half2(p0, p1);
+                    }
+                }
+                tmem_st_32x32(p_tmem + b * 32, pk);
+                float sum, sum_hi;
+                unpack_f32x2(sum2, sum, sum_hi);
+                l += sum + sum_hi;
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[b]);
+            }
+            // tile epilogue: O is complete once the last P.V has landed; read it out and hand TMEM back at once
+            mbar_wait(o_done, ti & 1);
+            tc_fence_after();
+            float o_acc[ATT_D];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(o_tmem + c * 32, r);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = __uint_as_float(r[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_free);
+            const int qrow = slab * ATT_BQ + row;
+            if (qrow < p.n_q) {
+                const float inv = p.out_weight / l;
+                __half* op = p.out + (long long)p.out_b[item] * p.out_bs + (long long)qrow * p.out_ld + p.out_col0 +
+                             head * ATT_D;
+                uint4* op4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = o_acc[t * 8 + i] * inv;
+                    if (p.accumulate) {
+                        const uint4 u = op4[t];
+                        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 f = __half22float2(h2[i]);
+                            v[2 * i] += f.x;
+                            v[2 * i + 1] += f.y;
+                        }
+                    }
+                    op4[t] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
+                                        pack_half2(v[6], v[7]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Two-stream variant (self-attention): the softmax at head_dim 64 is bound by instruction latency, not by a pipe - with
@@ -906,11 +1201,25 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
     static int force_g = 0;
     static int two_stream_min_kv = 1 << 30;
     static bool cross_kernel = true;
+    static bool persistent = true;
+    static int p_stages = 0;
+    static int num_sms = 148;
     if (!configured) {
         OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1, 3>::SMEM));
         OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1, 5>::SMEM));
         OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2, 6>::SMEM));
         OMG_CUDA(cudaFuncSetAttribute(attn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Att2Cfg::SMEM));
+        OMG_CUDA(cudaFuncSetAttribute(attn_p_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttPCfg<5, 2>::SMEM));
+        OMG_CUDA(cudaFuncSetAttribute(attn_p_kernel<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttPCfg<6, 1>::SMEM));
+        const char* e7 = getenv("OMG_ATTN_PSTAGES");  // 5 | 6: force the (KV stages, Q buffers) = (5, 2) | (6, 1) variant
+        p_stages = e7 ? atoi(e7) : 0;
+        const char* e6 = getenv("OMG_ATTN_PERSISTENT");  // 0: one CTA per tile
+        persistent = !(e6 && atoi(e6) == 0);
+        {
+            int dev = 0;
+            OMG_CUDA(cudaGetDevice(&dev));
+            OMG_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        }
         const char* e = getenv("OMG_ATTN_TILES");  // 1 | 2: force the tiles-per-CTA variant (measurements)
         force_g = e ? atoi(e) : 0;
         const char* e3 = getenv("OMG_ATTN_CROSS");  // 0: cross-attention through the per-(tile, head) kernel
@@ -964,6 +1273,17 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
         if (d->n_kv <= 16) return launch_cross<16>(p, d, stream, max_qb, max_kb, max_vb);
         if (d->n_kv <= 80) return launch_cross<80>(p, d, stream, max_qb, max_kb, max_vb);
         return launch_cross<128>(p, d, stream, max_qb, max_kb, max_vb);
+    }
+    if (!force_g && persistent && d->n_kv > 2 * ATT_BKV && d->n_kv < two_stream_min_kv) {
+        const int n_slabs = (d->n_q + ATT_BQ - 1) / ATT_BQ;
+        const int n_tiles = n_slabs * d->heads * d->n_items;
+        const int grid = std::min(n_tiles, 2 * num_sms);
+        const bool deep = p_stages == 6 || (p_stages == 0 && false);
+        if (deep)
+            OMG_CUDA(launch_pdl(attn_p_kernel<6, 1>, dim3(grid), dim3(256), AttPCfg<6, 1>::SMEM, stream, p, n_tiles, n_slabs));
+        else
+            OMG_CUDA(launch_pdl(attn_p_kernel<5, 2>, dim3(grid), dim3(256), AttPCfg<5, 2>::SMEM, stream, p, n_tiles, n_slabs));
+        return check_launch("attn_p_kernel");
     }
     if (!force_g && d->n_kv >= two_stream_min_kv) {
         dim3 grid((d->n_q + ATT_BQ - 1) / ATT_BQ, d->heads, d->n_items);

@@ -196,6 +196,27 @@ def test_cross_attention_head_group_kernel(ops, B, n_q, n_kv, heads):
     assert rel(out2, base.float() + 0.8 * ref) < 2e-3
 
 
+@pytest.mark.parametrize("B,N,n_kv,heads", [(4, 1024, 1024, 20), (2, 2048, 320, 8), (3, 640, 200, 5), (1, 4096, 4096, 3)])
+def test_self_attention_persistent_many_tiles(ops, B, N, n_kv, heads):
+    """The persistent self-attention kernel: 2 x #SM CTAs walk several tiles each as one stream of KV blocks (barrier
+    phases run across tile boundaries, Q double-buffered, O handed back through o_free): more tiles than CTAs, odd block
+    counts per tile, a partial last block, remapped batch rows and the accumulate term."""
+    Cc = heads * 64
+    q = rnd(B, N, Cc, seed=41) * 1.5
+    kv = rnd(B, n_kv, 2 * Cc, seed=42)
+    kv[..., :Cc] *= 1.5
+    out = torch.empty(B, N, Cc, device="cuda", dtype=torch.float16)
+    items = [(b, (b + 1) % B, (b + 1) % B, b) for b in range(B)]
+    ops.attention(q, kv, kv, out, heads, N, n_kv, items, k_col0=0, v_col0=Cc)
+    idx = [(b + 1) % B for b in range(B)]
+    ref = _attn_ref(q[idx], kv[idx][..., :Cc], kv[..., Cc:], heads, 0.125)
+    assert rel(out, ref) < 2e-3
+    base = rnd(B, N, Cc, seed=43)
+    out2 = base.clone()
+    ops.attention(q, kv, kv, out2, heads, N, n_kv, items, k_col0=0, v_col0=Cc, out_weight=0.7, accumulate=True)
+    assert rel(out2, base.float() + 0.7 * ref) < 2e-3
+
+
 def test_attention_p2p_remap_and_cross(ops):
     B, N, heads, Lk = 4, 1024, 10, 77
     Cc = heads * 64
