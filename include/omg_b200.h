@@ -37,7 +37,7 @@ typedef struct {
     int32_t b_idx; /* 0: columns of w, 1: columns of w2 (e.g. the LoRA up-projection B, kept un-merged) */
 } omg_seg;
 
-enum { OMG_EPI_NONE = 0, OMG_EPI_GEGLU = 1, OMG_EPI_SILU = 2, OMG_EPI_QUICK_GELU = 3, OMG_EPI_GELU = 4 };
+enum { OMG_EPI_NONE = 0, OMG_EPI_GEGLU = 1, OMG_EPI_SILU = 2, OMG_EPI_QUICK_GELU = 3, OMG_EPI_GELU = 4, OMG_EPI_GELU_TANH = 5 };
 
 /*
  * out[pix, n] = epi( sum_seg sum_k A_seg[pix+(dx,dy), k] * W[n, b_k0+k] + bias[n] + rowvec[b, n] ) + residual[pix, n]
@@ -210,6 +210,24 @@ int omg_axpy(const void* a, const void* b, float alpha, void* y, long long n, vo
  * 512 channels: `Attention(heads=1)` inside diffusers' AutoencoderKL, reached from src/pipelines/lora_pipeline.py:649)
  * materialises its scores with omg_gemm, normalises them here and applies them with a second omg_gemm. */
 int omg_softmax_rows(void* x, long long rows, int cols, long long ld, float scale, void* stream);
+
+/*
+ * EfficientViT-SAM image encoder (the segmentation model between the two stages), the ops that are not
+ * GEMM-shaped.  Channels-last fp16, fp32 arithmetic.  Dense convolutions of the encoder go through omg_gemm (BatchNorm
+ * folded into the weights, OMG_EPI_GELU_TANH), LayerNorm2d through omg_layernorm.
+ *   omg_dwconv: depthwise k x k (3 | 5) convolution, stride 1 | 2, "same" padding, + bias, act 1 = tanh-GELU; w is
+ *     tap-major [k*k, C]; x / y rows of ldx / ldy elements (MBConv.depth_conv, LiteMLA.aggreg[.][0];
+ *     src/efficientvit/models/nn/ops.py:196-241,371-392).
+ *   omg_group1x1: grouped 1x1 convolution with square groups of 32 channels, w [C, 32] (LiteMLA.aggreg[.][1]).
+ *   omg_relu_linear_attention: LiteMLA.relu_linear_att (ops.py:404-440): per head (q | k | v, dim 32)
+ *     out = relu(q) (relu(k)^T [v | 1]) normalised by its last column + eps; qkv [B, N, heads*96] -> out [B, N, heads*32].
+ *   omg_resize_bicubic: F.interpolate(mode="bicubic", align_corners=False) (SamNeck inputs, sam.py:117-123).
+ */
+int omg_dwconv(const void* x, const void* w, const void* bias, void* y, int B, int H, int W, int C, int ldx, int ldy, int ksize,
+               int stride, int act, void* stream);
+int omg_group1x1(const void* x, const void* w, void* y, long long pixels, int C, int ldx, int ldy, int group, void* stream);
+int omg_relu_linear_attention(const void* qkv, void* out, int B, int N, int heads, int dim, float eps, void* stream);
+int omg_resize_bicubic(const void* x, void* y, int B, int H, int W, int C, int Ho, int Wo, void* stream);
 
 /* Error string of the last failing call on this thread (never NULL). */
 const char* omg_last_error(void);

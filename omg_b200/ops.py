@@ -255,6 +255,54 @@ def groupnorm_apply(x1, part1, gamma, beta, eps, silu, x2=None, part2=None, out=
     return out
 
 
+def dwconv(x, w, bias=None, out=None, ksize=3, stride=1, act=0):
+    """Depthwise k x k conv ("same" padding) over (B, H, W, C) rows that may be strided views along the channel axis
+    (x.stride(2) = row stride); w tap-major [k*k, C]; act 1 = tanh-GELU."""
+    _chk16(x)
+    B, H, W, Cc = x.shape
+    assert x.stride(3) == 1 and x.stride(1) == x.stride(2) * W and x.stride(0) == x.stride(1) * H
+    Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cc), dtype=torch.float16, device=x.device)
+    assert out.stride(3) == 1 and out.stride(1) == out.stride(2) * Wo and out.stride(0) == out.stride(1) * Ho
+    L.check(L.load().omg_dwconv(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), B, H, W, Cc, x.stride(2), out.stride(2),
+                                ksize, stride, int(act), _stream()), "omg_dwconv")
+    return out
+
+
+def group1x1(x, w, out):
+    """Grouped 1x1 conv, square groups of 32 channels: x (.., C) rows strided, w [C, 32], out (.., C) rows strided."""
+    _chk16(x)
+    Cc = x.shape[-1]
+    pixels = x.numel() // Cc
+    L.check(L.load().omg_group1x1(x.data_ptr(), w.data_ptr(), out.data_ptr(), pixels, Cc, x.stride(-2), out.stride(-2), 32, _stream()),
+            "omg_group1x1")
+    return out
+
+
+def relu_linear_attention(qkv, heads, dim=32, eps=1e-15, out=None):
+    """LiteMLA core: qkv (B, N, heads*3*dim) contiguous -> (B, N, heads*dim)."""
+    _chk16(qkv)
+    assert qkv.is_contiguous()
+    B, N, _ = qkv.shape
+    if out is None:
+        out = torch.empty((B, N, heads * dim), dtype=torch.float16, device=qkv.device)
+    L.check(L.load().omg_relu_linear_attention(qkv.data_ptr(), out.data_ptr(), B, N, heads, dim, float(eps), _stream()),
+            "omg_relu_linear_attention")
+    return out
+
+
+def resize_bicubic(x, Ho, Wo, out=None):
+    """F.interpolate(mode='bicubic', align_corners=False) over (B, H, W, C)."""
+    _chk16(x)
+    assert x.is_contiguous()
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cc), dtype=torch.float16, device=x.device)
+    L.check(L.load().omg_resize_bicubic(x.data_ptr(), out.data_ptr(), B, H, W, Cc, Ho, Wo, _stream()), "omg_resize_bicubic")
+    return out
+
+
 def layernorm(x, gamma, beta, eps=1e-5, out=None):
     _chk16(x)
     assert x.is_contiguous()

@@ -19,6 +19,11 @@ Fixtures (all fp32, fixed seeds):
   fusion_iid.pt    the same statements of InstantidMultiConceptPipeline.__call__ (src/pipelines/instantid_pipeline.py:
                    618-686): every call the block makes to the IdentityNet and to the concept UNet is recorded
                    (inputs, face / text tokens, condition image, scale, residual hand-over), plus the fused noise.
+  sam_encoder.pt   EfficientViTSamImageEncoder (src/efficientvit/models/efficientvit/sam.py:176-192: EfficientViTLargeBackbone
+                   with the xl1 block layout res/fmb/fmb/fmb/att@3/att@3 at narrow widths -> SamNeck -> LayerNorm2d), the
+                   unmodified modules imported with stubs for the packages their unrelated imports need (timm, onnx,
+                   segment_anything, torchvision: training apps and the mask decoder), random BatchNorm statistics,
+                   norm eps 1e-6 like sam_model_zoo.py:44; plus one LiteMLA and one EfficientViTBlock on their own.
   kps.npz          draw_kps_multi (inference_instantid.py:127-156, extracted from the file by ast: the module itself
                    imports diffusers) on three faces at 256 x 256.
 """
@@ -387,7 +392,89 @@ def make_cli_flags():
         json.dump(out, f, indent=1, sort_keys=True)
 
 
+def _import_efficientvit():
+    """The reference's EfficientViT modules; packages that only its training apps / mask decoder import are stubbed."""
+    import importlib
+    import types
+
+    class Stub(types.ModuleType):
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return type(k, (), {})
+
+    importlib.import_module("src")
+    importlib.import_module("src.efficientvit")
+    for name in ["src.efficientvit.apps.trainer.run_config", "segment_anything.modeling.mask_decoder",
+                 "segment_anything.modeling.prompt_encoder", "segment_anything.utils.amg", "segment_anything.utils.transforms",
+                 "torchvision.transforms.functional", "timm", "onnx"]:
+        parts = name.split(".")
+        for i in range(1, len(parts) + 1):
+            n = ".".join(parts[:i])
+            if n not in sys.modules:
+                m = Stub(n)
+                m.__path__ = []
+                sys.modules[n] = m
+    from src.efficientvit.models.efficientvit import sam as S
+    from src.efficientvit.models.efficientvit.backbone import EfficientViTLargeBackbone
+    from src.efficientvit.models.nn import ops as O
+    from src.efficientvit.models.nn.norm import set_norm_eps
+    return S, EfficientViTLargeBackbone, O, set_norm_eps
+
+
+def _randomise_bn(module, g):
+    for m in module.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+            m.weight.data.copy_(1.0 + 0.2 * torch.randn(m.weight.shape, generator=g))
+            m.bias.data.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+
+
+def make_sam_encoder():
+    S, Backbone, O, set_norm_eps = _import_efficientvit()
+    g = torch.Generator().manual_seed(0)
+    torch.manual_seed(0)
+    # the xl1 layout (sam.py:630-652) at narrow widths; every width a multiple of 32 (LiteMLA heads of 32 channels)
+    bb = Backbone(width_list=[32, 32, 64, 64, 128, 128], depth_list=[1, 1, 1, 1, 2, 1],
+                  block_list=["res", "fmb", "fmb", "fmb", "att@3", "att@3"], expand_list=[1, 4, 4, 4, 4, 6],
+                  fewer_norm_list=[False, False, False, False, True, True])
+    neck = S.SamNeck(fid_list=["stage5", "stage4", "stage3"], in_channel_list=[128, 128, 64], head_width=64, head_depth=2,
+                     expand_ratio=4, middle_op="fmb")
+    enc = S.EfficientViTSamImageEncoder(bb, neck).eval()
+    set_norm_eps(enc, 1e-6)                                    # sam_model_zoo.py:44
+    _randomise_bn(enc, g)
+    for p in enc.parameters():                                 # fp16-representable weights (the kernels store fp16)
+        p.data = p.data.half().float()
+    enc.norm.weight.data.copy_((1.0 + 0.1 * torch.randn(256, generator=g)).half().float())
+    enc.norm.bias.data.copy_((0.1 * torch.randn(256, generator=g)).half().float())
+    x = torch.randn(1, 3, 384, 384, generator=g).half().float()   # stage3 48^2 / stage4 24^2 / stage5 12^2 -> 64^2 (bicubic up)
+    with torch.no_grad():
+        feats = bb(x)
+        y = enc(x)
+    sd = {k: (v.half() if v.is_floating_point() else v) for k, v in enc.state_dict().items() if "num_batches" not in k}
+    # one LiteMLA with the 5x5 aggregation of the smaller zoo models, and one EfficientViTBlock, on their own
+    mla = O.LiteMLA(64, 64, dim=32, scales=(5,), norm=(None, "bn2d")).eval()
+    blk = O.EfficientViTBlock(96, dim=32, expand_ratio=4, scales=(3,), norm="bn2d", act_func="gelu").eval()
+    for m in (mla, blk):
+        set_norm_eps(m, 1e-6)
+        _randomise_bn(m, g)
+        for p in m.parameters():
+            p.data = p.data.half().float()
+    xm = torch.randn(2, 64, 24, 20, generator=g).half().float()
+    xb = torch.randn(1, 96, 16, 16, generator=g).half().float()
+    with torch.no_grad():
+        ym, yb = mla(xm), blk(xb)
+    torch.save({"sd": sd, "x": x.half(), "y": y.half(), "stage_shapes": {k: tuple(v.shape) for k, v in feats.items()},
+                "stage5": feats["stage5"].half(), "stage3": feats["stage3"].half(),
+                "mla_sd": {k: v.half() if v.is_floating_point() else v for k, v in mla.state_dict().items() if "num_batches" not in k},
+                "mla_x": xm.half(), "mla_y": ym.half(),
+                "blk_sd": {k: v.half() if v.is_floating_point() else v for k, v in blk.state_dict().items() if "num_batches" not in k},
+                "blk_x": xb.half(), "blk_y": yb.half()}, os.path.join(OUT, "sam_encoder.pt"))
+
+
 if __name__ == "__main__":
+    make_sam_encoder()
     make_cli_flags()
     make_fusion_instantid()
     make_region_attn()
