@@ -87,7 +87,7 @@ def test_lite_mla_and_efficientvit_block_match_the_reference_modules():
     y = efficientvit_block({"b." + k: v for k, v in d["blk_sd"].items()}, "b", to(d["blk_x"]))
     e2 = rel(y.permute(0, 3, 1, 2), d["blk_y"])
     print("LiteMLA rel err", e1, "EfficientViTBlock rel err", e2)
-    assert e1 < 3e-3 and e2 < 3e-3
+    assert e1 < 5e-4 and e2 < 5e-4   # measured 3.6e-4 / 3.6e-4
 
 
 def test_sam_image_encoder_matches_the_reference_module():
@@ -100,4 +100,4 @@ def test_sam_image_encoder_matches_the_reference_module():
                                                                          if k.startswith("stage") and k != "stage_final"}
     e3, e5, e = rel(feats[3], d["stage3"]), rel(feats[5], d["stage5"]), rel(y, d["y"])
     print("sam encoder rel err: stage3", e3, "stage5", e5, "output", e)
-    assert e3 < 3e-3 and e5 < 5e-3 and e < 5e-3
+    assert e3 < 5.5e-4 and e5 < 6e-4 and e < 8.5e-4   # measured 4.1e-4 / 4.5e-4 / 6.5e-4
