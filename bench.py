@@ -368,7 +368,7 @@ def _main():
         traffic = None
         try:  # measured DRAM bytes per launch of the same forward (ncu launch list committed under profiles/)
             from scripts.summarize_launches import summarize
-            n_l, traffic = summarize(os.path.join(ROOT, "profiles", "r01_launches_main_unet_b4.csv"), os.devnull, "")
+            n_l, traffic = summarize(os.path.join(ROOT, "profiles", "r02_launches_main_unet_b4.csv"), os.devnull, "")
         except Exception:
             traffic = None
         flops_img = SAMPLE_FORWARDS_PER_IMAGE * unet_flops(cfg, IMAGE // 8, IMAGE // 8)
@@ -382,7 +382,7 @@ def _main():
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "kernel": "gemm_tc_kernel",
                          "traffic_note": "dram__bytes_read+write per launch, mean over the 488 gemm_tc_kernel launches of one "
-                                         "main-UNet forward, ncu cold-cache pass (profiles/r01_launches_main_unet_b4.csv)",
+                                         "main-UNet forward, ncu cold-cache pass (profiles/r02_launches_main_unet_b4.csv)",
                          "algorithmic_bytes_per_launch": sum(p[3] for p in prof) / max(len(prof), 1),
                          "algorithmic_flops_per_launch": g_flops / max(len(prof), 1),
                          "launches_profiled": len(prof),

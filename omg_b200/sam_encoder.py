@@ -217,7 +217,7 @@ class PackedSamImageEncoder:
         return convs[-1](h, residual=x if residual else None)
 
     @torch.no_grad()
-    def __call__(self, image: torch.Tensor, return_features: bool = False):
+    def __call__(self, image: torch.Tensor, return_features: bool = False, out_dtype: Optional[torch.dtype] = None):
         """image (B, 3, H, W) normalised like SamResize / transforms.Normalize produce it -> (B, 256, 64, 64) fp16
         [, {stage index: (B, C, h, w) backbone features}]."""
         x = image.to(self.dev, torch.float16).permute(0, 2, 3, 1)
@@ -245,6 +245,8 @@ class PackedSamImageEncoder:
         x = self.neck_out(x)
         B, H, W, C = x.shape
         y = ops.layernorm(x.view(B * H * W, C), self.ln[0], self.ln[1], eps=self.eps).view(B, H, W, C).permute(0, 3, 1, 2)
+        if out_dtype is not None:   # the reference's prompt encoder / mask decoder run in the model's dtype (fp32 in the CLI)
+            y = y.to(out_dtype)
         if return_features:
             return y, {k: v.permute(0, 3, 1, 2) for k, v in feats.items()}
         return y
