@@ -97,6 +97,14 @@ typedef struct {
      * concatenation of two producers - so GroupNorm never re-reads its input for statistics.  Not with GEGLU. */
     void* col_stats_out;
     int32_t col_stats_rb0, col_stats_rb_total;
+    /* fp32 master copy of the residual trunk (x <- x + f(x) through ~70 transformer blocks and the ResBlocks): the addend
+     * is read from residual_f32 [pixels, residual_f32_ld] instead of the fp16 `residual`, and the result is ALSO written as
+     * fp32 to out_f32 [pixels, out_f32_ld] (the fp16 output stays what the next GEMM / norm reads), so rounding to fp16
+     * no longer accumulates along the chain.  Either may be NULL.  Contiguous output view, N % 32 == 0, not with GEGLU. */
+    const void* residual_f32;
+    int64_t residual_f32_ld;
+    void* out_f32;
+    int64_t out_f32_ld;
 } omg_gemm_desc;
 
 int omg_gemm(const omg_gemm_desc* desc, void* stream);

@@ -64,6 +64,13 @@ struct alignas(64) GemmParams {
     int n_col_groups;          // c1/c2 are [n_col_groups][N]; row group g = rows [col_group_end[g-1], col_group_end[g])
     long long col_group_end[8];
     int w_group_rows;          // > 0: the weight matrix holds one [N, K] plane per row group (per-stream merged LoRA)
+    // fp32 master copy of the residual trunk: the addend is read from / the result also written to fp32 twins, so the
+    // chain h <- h + f(h) accumulates in fp32 while every GEMM / norm input stays the fp16 copy
+    int gelu_exact;            // 1: libdevice erff (FMA pipe only) instead of the two-MUFU form; set for short-K launches
+    const float* residual_f32;
+    long long residual_f32_ld;
+    float* out_f32;
+    long long out_f32_ld;
     float4* col_stats;         // GroupNorm statistics of the output: [B][cs_rb_total][N] float2 (sum, sumsq), or null
     int cs_rb0, cs_rb_total;
 };
@@ -103,7 +110,8 @@ struct GemmCfg {
 // kernels under the power cap).
 __device__ __forceinline__ float gelu_erf(float x) {
     const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));  // MUFU.RCP (1 ulp); __frcp_rn is a slow exact sequence
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
@@ -398,7 +406,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                             a = __uint_as_float(r[i]) + sb[off + i];
                             g = __uint_as_float(r[i + 1]) + sb[off + i + 1];
                         }
-                        return a * gelu_erf(g);
+                        return a * (p.gelu_exact ? 0.5f * g * (1.0f + erff(g * 0.70710678118654752f)) : gelu_erf(g));
                     };
 #pragma unroll
                     for (int j = 0; j < 8; ++j)  // columns (4j, 4j+1) and (4j+2, 4j+3) are (value, gate) pairs
@@ -449,6 +457,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                             }
                         }
                         load_res(c + 2 * CH_STEP, resb);
+                    }
+                    if (p.residual_f32 != nullptr && row_valid) {  // fp32 addend (L2-resident: written by the previous GEMM of the chain)
+                        const float4* rp = reinterpret_cast<const float4*>(p.residual_f32 + pix * (size_t)p.residual_f32_ld + nacc0);
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 f = __ldg(rp + j4);
+                            v[j4 * 4] += f.x;
+                            v[j4 * 4 + 1] += f.y;
+                            v[j4 * 4 + 2] += f.z;
+                            v[j4 * 4 + 3] += f.w;
+                        }
+                    }
+                    if (p.out_f32 != nullptr && row_valid) {
+                        float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * (size_t)p.out_f32_ld + nacc0);
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
                     }
                     if (p.stats_out != nullptr) {
                         if (nacc0 + 32 <= p.N) {
@@ -756,6 +780,16 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     OMG_CHECK(!p.stats_in || (p.col_c1 && p.col_c2 && d->ln_dim > 0 && d->row_stats_parts >= 1 && !d->rowvec),
               "omg_gemm: folded LayerNorm needs col_c1, col_c2, ln_dim, row_stats_parts and no rowvec");
     OMG_CHECK(!p.stats_out || !geglu, "omg_gemm: row statistics cannot be emitted by the GEGLU epilogue");
+    p.residual_f32 = static_cast<const float*>(d->residual_f32);
+    p.residual_f32_ld = d->residual_f32_ld;
+    p.out_f32 = static_cast<float*>(d->out_f32);
+    p.out_f32_ld = d->out_f32_ld;
+    OMG_CHECK((!p.residual_f32 && !p.out_f32) || (!geglu && d->N % 32 == 0 && !(d->residual && d->residual_f32)),
+              "omg_gemm: fp32 residual / output twins need a non-GEGLU epilogue, N %% 32 == 0, and replace the fp16 residual");
+    OMG_CHECK((!p.residual_f32 || d->residual_f32_ld % 4 == 0) && (!p.out_f32 || d->out_f32_ld % 4 == 0),
+              "omg_gemm: fp32 twin row strides must be multiples of 4");
+    OMG_CHECK((!p.residual_f32 && !p.out_f32) || (d->d.sw == d->d.C && d->d.sh == (int64_t)d->d.sw * W && d->d.sb == d->d.sh * H),
+              "omg_gemm: fp32 twins need a contiguous output view (rows are indexed by pixel)");
     p.col_stats = static_cast<float4*>(d->col_stats_out);
     p.cs_rb0 = d->col_stats_rb0;
     p.cs_rb_total = d->col_stats_rb_total;
@@ -807,6 +841,10 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     // the TMA box of the weight tile is this CTA's slice: BN rows, or BN/2 for a CTA pair
     long k_blocks = 0;
     for (int i = 0; i < p.n_segs; ++i) k_blocks += p.segs[i].k_blocks;
+    // GEGLU epilogue: with K <= 960 the epilogue, not the mainloop, bounds the tile and the two MUFU ops per gate of
+    // gelu_erf (quarter-rate unit) cost more than erff's ~30 FMA-pipe instructions (measured, same box: 16384 x 5120 x 640
+    // 148 vs 159 us; 4096 x 10240 x 1280 the other way round: 98 vs 93 us)
+    p.gelu_exact = k_blocks < 16 ? 1 : 0;
     bool pair_ok = true;  // both CTAs of a pair must belong to the same stream
     for (int i = 0; i + 1 < p.n_col_groups; ++i) pair_ok = pair_ok && (p.col_group_end[i] % 256 == 0);
     // BN = 160 pairs are available on request but never chosen: measured 0..-8 % (profiles/r01_kernel_bench.json)

@@ -35,8 +35,13 @@ def _ptr(t):
 
 
 def gemm(a_views, segs, w, N, Ktot, d_view, bias=None, rowvec=None, rowvec_ld=0, residual=None, residual_ld=0,
-         epilogue=L.EPI_NONE, block_n=0, w2=None, stats_out=None, ln=None, cta_pair=0, row_groups=None, colstats=None):
+         epilogue=L.EPI_NONE, block_n=0, w2=None, stats_out=None, ln=None, cta_pair=0, row_groups=None, colstats=None,
+         residual_f32=None, out_f32=None):
     d = L.GemmDesc()
+    if residual_f32 is not None:   # [pixels, N] fp32 twins of the residual trunk (see omg_gemm_desc)
+        d.residual_f32, d.residual_f32_ld = residual_f32.data_ptr(), residual_f32.stride(-2)
+    if out_f32 is not None:
+        d.out_f32, d.out_f32_ld = out_f32.data_ptr(), out_f32.stride(-2)
     d.cta_pair = cta_pair
     if colstats is not None:  # (partials [B, rb_total, N, 2] fp32, first block this launch fills)
         part, rb0 = colstats
@@ -89,7 +94,7 @@ def colstats_blocks(W, H=1):
 
 
 def linear(x, w, bias=None, residual=None, out=None, epilogue=L.EPI_NONE, extra=None, block_n=0, lora=None,
-           stats_out=None, ln=None, cta_pair=0, row_groups=None, colstats=None):
+           stats_out=None, ln=None, cta_pair=0, row_groups=None, colstats=None, residual_f32=None, out_f32=None):
     """out[M, N'] = epi(x[M,K] @ w[N, :K]^T (+ extra K-segments) + bias) + residual.
 
     `extra` = list of (tensor [M,Ki], column offset into w): further K-segments of the same weight matrix.
@@ -118,7 +123,8 @@ def linear(x, w, bias=None, residual=None, out=None, epilogue=L.EPI_NONE, extra=
     cs = None if colstats is None else (colstats.view(1, -1, colstats.shape[2], 2), 0)
     gemm(views, segs, w, N, Ktot, view4(out), bias=bias, residual=residual,
          residual_ld=0 if residual is None else residual.stride(0), epilogue=epilogue, block_n=block_n, w2=w2,
-         stats_out=stats_out, ln=ln, cta_pair=cta_pair, row_groups=row_groups, colstats=cs)
+         stats_out=stats_out, ln=ln, cta_pair=cta_pair, row_groups=row_groups, colstats=cs,
+         residual_f32=residual_f32, out_f32=out_f32)
     return out
 
 
@@ -126,7 +132,8 @@ def _taps3x3(Cin, a_idx=0, c0=0, k0=0):
     return [(a_idx, kx - 1, ky - 1, c0, Cin, k0 + (ky * 3 + kx) * Cin) for ky in range(3) for kx in range(3)]
 
 
-def conv3x3(x, w, bias=None, rowvec=None, residual=None, out=None, shortcut=None, block_n=0, cta_pair=0, colstats=None):
+def conv3x3(x, w, bias=None, rowvec=None, residual=None, out=None, shortcut=None, block_n=0, cta_pair=0, colstats=None,
+            residual_f32=None, out_f32=None):
     """3x3 / stride 1 / pad 1 conv over (B,H,W,Cin).  w = [N, 9*Cin (+ shortcut K)] packed (ky, kx, c).
 
     shortcut = list of (tensor (B,H,W,Ci), weight column offset): 1x1-conv K-segments added to the same accumulator
@@ -144,7 +151,7 @@ def conv3x3(x, w, bias=None, rowvec=None, residual=None, out=None, shortcut=None
     gemm(views, segs, w, N, Ktot, view4(out), bias=bias, rowvec=rowvec,
          rowvec_ld=0 if rowvec is None else rowvec.stride(0),
          residual=residual, residual_ld=0 if residual is None else N, block_n=block_n, cta_pair=cta_pair,
-         colstats=None if colstats is None else (colstats, 0))
+         colstats=None if colstats is None else (colstats, 0), residual_f32=residual_f32, out_f32=out_f32)
     return out
 
 

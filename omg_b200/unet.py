@@ -275,6 +275,9 @@ class UNetRunner:
         self.merge_lora = os.environ.get("OMG_LORA", "merged") != "unmerged"
         # GroupNorm statistics come out of the producing conv / GEMM epilogue (OMG_GN_FUSE=0: statistics pass per norm)
         self.gn_fuse = os.environ.get("OMG_GN_FUSE", "1") != "0"
+        # fp32 master copy of the residual trunk (every tensor that is later a residual addend has an fp32 twin, written
+        # by the GEMM that produces it): rounding to fp16 no longer accumulates over the ~70 blocks (OMG_TRUNK_F32=0: off)
+        self.trunk_f32 = os.environ.get("OMG_TRUNK_F32", "1") != "0"
         self.dev = model.device
         self.ws: Dict[str, torch.Tensor] = {}
         self.use_graphs = use_graphs
@@ -335,6 +338,19 @@ class UNetRunner:
         part = self._alloc(f"cs.{t.data_ptr()}", (t.shape[0], rb, t.shape[-1], 2), torch.float32, False)
         t._cs = part
         return part
+
+    def _twin(self, t: torch.Tensor):
+        """fp32 twin [pixels, C] of the trunk tensor `t`, found later as `t._f32`."""
+        if not self.trunk_f32:
+            return None
+        tw = self._alloc(f"f32.{t.data_ptr()}", (t.numel() // t.shape[-1], t.shape[-1]), torch.float32, False)
+        t._f32 = tw
+        return tw
+
+    def _res(self, x):
+        """(fp16 residual, fp32 residual) arguments for a GEMM that adds the trunk tensor x."""
+        tw = getattr(x, "_f32", None) if self.trunk_f32 else None
+        return (None, tw) if tw is not None else (x, None)
 
     def _gn(self, x, gamma, beta, eps, silu, out, x2=None):
         p1 = getattr(x, "_cs", None)
@@ -404,7 +420,7 @@ class UNetRunner:
         return res
 
     def _lin(self, key, x2d, out, bias=None, residual=None, epilogue=L.EPI_NONE, groups=None, rows_per_item=None,
-             stats_out=None, ln=None, colstats=None):
+             stats_out=None, ln=None, colstats=None, residual_f32=None, out_f32=None):
         """Linear with the un-merged LoRA deltas of every row group: t[rows_g, cols_g] = x[rows_g] A_g^T (skinny
         GEMMs, the other blocks of t stay zero), then ONE GEMM over all rows whose extra K-segment is t against
         [s B_1 | s B_2 | ...].  ln = (row statistics, parts, channels): the input's LayerNorm is folded into this
@@ -424,7 +440,7 @@ class UNetRunner:
             ln_arg = (stats, parts, M, 0, dim, 1e-5, c1, c2, ends)
         if not active:
             return ops.linear(x2d, w, bias=bias, residual=residual, out=out, epilogue=epilogue, stats_out=stats_out,
-                              ln=ln_arg, colstats=colstats)
+                              ln=ln_arg, colstats=colstats, residual_f32=residual_f32, out_f32=out_f32)
         base = groups[0].start
         ends = [(g.stop - base) * n for g in groups]
         if self.merge_lora and groups is self.groups and len(groups) <= 8 and all(e % 128 == 0 for e in ends[:-1]):
@@ -434,7 +450,7 @@ class UNetRunner:
             if ln is not None:
                 ln_arg = (ln[0], ln[1], M, 0, ln[2], 1e-5, c1m, c2m, ends)
             return ops.linear(x2d, wm, bias=bias, residual=residual, out=out, epilogue=epilogue, stats_out=stats_out,
-                              ln=ln_arg, row_groups=ends, colstats=colstats)
+                              ln=ln_arg, row_groups=ends, colstats=colstats, residual_f32=residual_f32, out_f32=out_f32)
         a_idx = 2 if ln is not None else 0   # gamma-folded A for LayerNorm consumers
         r_tot = sum(e[0].shape[0] for _, e in active)
         sig = ",".join(f"{g.start}-{g.stop}:{e[0].shape[0]}" for g, e in active)
@@ -451,7 +467,7 @@ class UNetRunner:
             ops.linear(x2d[r0:r1], e[a_idx], out=t[r0:r1, c0:c0 + e[0].shape[0]])
             c0 += e[0].shape[0]
         return ops.linear(x2d, w, bias=bias, residual=residual, out=out, epilogue=epilogue, lora=(t, b2),
-                          stats_out=stats_out, ln=ln_arg, colstats=colstats)
+                          stats_out=stats_out, ln=ln_arg, colstats=colstats, residual_f32=residual_f32, out_f32=out_f32)
 
     # ------------------------------------------------------------------------------------------- per-call setup
     def set_conditioning(self, timesteps, ctx, text_embeds: torch.Tensor, time_ids: torch.Tensor,
@@ -563,8 +579,11 @@ class UNetRunner:
         cs = self._cs(out, W, H)
         if P[name + ".w2"].shape[1] > 9 * cout:
             sc = [(x, 9 * cout)] + ([(skip, 9 * cout + C1)] if skip is not None else [])
-            return ops.conv3x3(a2, P[name + ".w2"], bias=P[name + ".bias2"], shortcut=sc, out=out, colstats=cs)
-        return ops.conv3x3(a2, P[name + ".w2"], bias=P[name + ".bias2"], residual=x, out=out, colstats=cs)
+            return ops.conv3x3(a2, P[name + ".w2"], bias=P[name + ".bias2"], shortcut=sc, out=out, colstats=cs,
+                               out_f32=self._twin(out))
+        r16, r32 = self._res(x)
+        return ops.conv3x3(a2, P[name + ".w2"], bias=P[name + ".bias2"], residual=r16, out=out, colstats=cs,
+                           residual_f32=r32, out_f32=self._twin(out))
 
     def _transformer(self, name, ch, layers, x, variant):
         P, m = self.m.p, self.m
@@ -583,7 +602,9 @@ class UNetRunner:
             parts = ops.gemm_plan(ch, L.EPI_NONE, M)[1]
             stats = self.fbuf(f"tr.rowstats.{ch}.{N}", (parts, M, 2))
             lnS = (stats, parts, ch)
-        self._lin(name + ".proj_in", n.view(M, ch), h, bias=P[name + ".proj_in.b"], stats_out=stats)
+        h32 = self._alloc(f"tr.h32.{ch}.{N}", (M, ch), torch.float32, False) if self.trunk_f32 else None
+        hres = dict(residual=h) if h32 is None else dict(residual_f32=h32, out_f32=h32)   # h <- h + f(h), in place
+        self._lin(name + ".proj_in", n.view(M, ch), h, bias=P[name + ".proj_in.b"], stats_out=stats, out_f32=h32)
         ln = self.buf(f"tr.ln.{ch}.{N}", (M, ch))
         qkv = self.buf(f"tr.qkv.{ch}.{N}", (B, N, 3 * ch))
         q = self.buf(f"tr.q.{ch}.{N}", (B, N, ch))
@@ -602,7 +623,7 @@ class UNetRunner:
             b = f"{name}.transformer_blocks.{k}"
             self._lin(b + ".attn1.qkv", normed(b, "norm1"), qkv.view(M, 3 * ch), ln=lnS)
             ops.attention(qkv, qkv, qkv, o, heads, N, N, self_items, 0, ch, 2 * ch, scale=scale)
-            self._lin(b + ".attn1.out", o.view(M, ch), h, bias=P[b + ".attn1.out.b"], residual=h, stats_out=stats)
+            self._lin(b + ".attn1.out", o.view(M, ch), h, bias=P[b + ".attn1.out.b"], stats_out=stats, **hres)
             self._lin(b + ".attn2.q", normed(b, "norm2"), q.view(M, ch), ln=lnS)
             kv = self.kv[b]
             for ti, (items, wgt) in enumerate(zip(variant["cross_items"], variant["cross_weights"])):
@@ -612,13 +633,15 @@ class UNetRunner:
                 kvi = self.kv_ip[b]
                 ops.attention(q, kvi, kvi, o, heads, N, m.ip_tokens, variant["ip_items"], 0, 0, ch, scale=scale,
                               out_weight=m.ip_scale, accumulate=True)
-            self._lin(b + ".attn2.out", o.view(M, ch), h, bias=P[b + ".attn2.out.b"], residual=h, stats_out=stats)
+            self._lin(b + ".attn2.out", o.view(M, ch), h, bias=P[b + ".attn2.out.b"], stats_out=stats, **hres)
             self._lin(b + ".ff1", normed(b, "norm3"), g, bias=P[b + ".ff1.b"], epilogue=L.EPI_GEGLU, ln=lnS)
-            self._lin(b + ".ff2", g, h, bias=P[b + ".ff2.b"], residual=h, stats_out=stats)
+            self._lin(b + ".ff2", g, h, bias=P[b + ".ff2.b"], stats_out=stats, **hres)
         out = self.buf(name + ".out", (B, H, W, ch))
         # the [M, ch] GEMM walks 128-token tiles: its per-32-row partials are per-image partials iff N % 128 == 0
         cs = self._cs(out, N, 1) if N % 128 == 0 else None
-        self._lin(name + ".proj_out", h, out.view(M, ch), bias=P[name + ".proj_out.b"], residual=x.view(M, ch), colstats=cs)
+        r16, r32 = self._res(x)
+        self._lin(name + ".proj_out", h, out.view(M, ch), bias=P[name + ".proj_out.b"], residual=None if r16 is None else r16.view(M, ch),
+                  colstats=cs, residual_f32=r32, out_f32=self._twin(out))
         return out
 
     def _encoder(self, h, variant):
@@ -647,7 +670,7 @@ class UNetRunner:
         m, cfg, P = self.m, self.m.cfg, self.m.p
         B, H, W = self.B, self.H, self.W
         h = self.buf("conv_in.out", (B, H, W, cfg.block_out_channels[0]))
-        ops.conv3x3(self.sample_in, P["conv_in.w"], bias=P["conv_in.b"], out=h, colstats=self._cs(h, W, H))
+        ops.conv3x3(self.sample_in, P["conv_in.w"], bias=P["conv_in.b"], out=h, colstats=self._cs(h, W, H), out_f32=self._twin(h))
         h, skips = self._encoder(h, variant)
         if variant.get("residuals", False):
             # ControlNet outputs * conditioning_scale, added in place to the rows of the stream they belong to.  Several
@@ -660,6 +683,7 @@ class UNetRunner:
                 for sk, r in zip(skips + [h], list(down_r) + [mid_r]):
                     dst = sk[r0:r0 + r.shape[0]]
                     ops.axpy(dst, r, r_scale, out=dst)
+                    sk._f32 = None   # the fp32 twin no longer matches (no later residual add reads these tensors)
                     part = getattr(sk, "_cs", None)
                     if part is not None:  # the producer's statistics no longer describe these images: recompute them
                         hw = sk.shape[1] * sk.shape[2]
@@ -688,7 +712,7 @@ class UNetRunner:
         # sample = conv_in(sample) + cond_embedding: the embedding is the GEMM epilogue residual
         h = self.buf("conv_in.out", (B, H, W, c0))
         ops.conv3x3(self.sample_in, P["conv_in.w"], bias=P["conv_in.b"], residual=self.cond_emb, out=h,
-                    colstats=self._cs(h, W, H))
+                    colstats=self._cs(h, W, H), out_f32=self._twin(h))
         h, skips = self._encoder(h, variant)
         outs = []
         for i, s in enumerate(skips):
