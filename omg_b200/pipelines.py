@@ -197,6 +197,9 @@ class _BasePipeline:
         self.dedup = False
         self._prefix: Optional[dict] = None
         self.sample_forwards = 0  # UNet sample-forwards executed by the last call (296 per image as-executed)
+        # accuracy / speed switch: fp32 master copy of the UNet's residual trunk (see UNetRunner.trunk_f32); None = the
+        # runner's default (OMG_TRUNK_F32)
+        self.trunk_f32: Optional[bool] = None
 
     @classmethod
     def from_pretrained(cls, pretrained_model, controlnet=None, torch_dtype=torch.float16, variant: Optional[str] = "fp16",
@@ -229,10 +232,12 @@ class _BasePipeline:
 
     # ---------------------------------------------------------------------------------------------- helpers
     def _runner(self, tag, model: PackedUNet, batch, h, w, lora_key=None, groups=None, tag_extra=None) -> UNetRunner:
-        key = (tag, id(model), batch, h, w, lora_key, tag_extra)
+        key = (tag, id(model), batch, h, w, lora_key, tag_extra, self.trunk_f32)
         r = self._runners.get(key)
         if r is None:
             r = UNetRunner(model, batch, h, w, lora_key=lora_key, use_graphs=self.use_graphs, groups=groups)
+            if self.trunk_f32 is not None:
+                r.trunk_f32 = bool(self.trunk_f32)
             self._runners[key] = r
         return r
 

@@ -75,7 +75,7 @@ def main():
     print(json.dumps({"variant": "fp16_eager", "noise_rel_l2": rel(eager.float(), ref),
                       "blocks": {k: round(rel(eager_rec[k], ref_rec[k]), 6) for k in ref_rec}}), flush=True)
     unet = PackedUNet(cfg, sd, device=dev)
-    for variant, env in (("default", {}), ("trunk_fp16_only", {"OMG_TRUNK_F32": "0"}), ("ln_fold_off", {"OMG_LN_FOLD": "0"})):
+    for variant, env in (("default", {}), ("trunk_fp32_twins", {"OMG_TRUNK_F32": "1"}), ("ln_fold_off", {"OMG_LN_FOLD": "0"})):
         for k, v in env.items():
             os.environ[k] = v
         r = UNetRunner(unet, B, H, W, use_graphs=False)

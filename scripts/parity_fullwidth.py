@@ -271,10 +271,14 @@ def main():
     ap.add_argument("configs", nargs="*", default=["2"])
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--trunk-f32", action="store_true", help="run the CUDA path with the fp32 master copy of the residual trunk")
     a = ap.parse_args()
+    if a.trunk_f32:
+        os.environ["OMG_TRUNK_F32"] = "1"
     f = open(a.out, "a") if a.out else None
 
     def emit(rec):
+        rec["trunk_f32"] = os.environ.get("OMG_TRUNK_F32", "0") == "1"
         line = json.dumps(rec)
         print(line, flush=True)
         if f:
