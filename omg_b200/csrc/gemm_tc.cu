@@ -375,19 +375,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 load_res(ch0, res[0]);
                 load_res(ch0 + CH_STEP, res[1]);
             }
-            // fp32 twin of the residual: one chunk ahead (the first before the accumulator is ready), so that its L2
-            // latency hides behind the mainloop / the previous chunk instead of stalling the exposed epilogue of tall tiles
-            float4 rf[8];
-            const bool has_rf = (EPI != OMG_EPI_GEGLU) && p.residual_f32 != nullptr && row_valid;
-            const float* rf_row = has_rf ? p.residual_f32 + pix * (size_t)p.residual_f32_ld + n0 : nullptr;
-            auto load_rf = [&](int c) {
-                if (has_rf && c < NCH && n0 + c * 32 < p.N) {
-                    const float4* rp = reinterpret_cast<const float4*>(rf_row + c * 32);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) rf[j] = __ldg(rp + j);
-                }
-            };
-            if constexpr (EPI != OMG_EPI_GEGLU) load_rf(ch0);
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
@@ -471,15 +458,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                         }
                         load_res(c + 2 * CH_STEP, resb);
                     }
-                    if (has_rf) {  // fp32 addend, fetched while the previous chunk was processed
+                    if (p.residual_f32 != nullptr && row_valid) {  // fp32 addend (prefetching it a chunk ahead was measured: no gain)
+                        const float4* rp = reinterpret_cast<const float4*>(p.residual_f32 + pix * (size_t)p.residual_f32_ld + nacc0);
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            v[j4 * 4] += rf[j4].x;
-                            v[j4 * 4 + 1] += rf[j4].y;
-                            v[j4 * 4 + 2] += rf[j4].z;
-                            v[j4 * 4 + 3] += rf[j4].w;
+                            const float4 f = __ldg(rp + j4);
+                            v[j4 * 4] += f.x;
+                            v[j4 * 4 + 1] += f.y;
+                            v[j4 * 4 + 2] += f.z;
+                            v[j4 * 4 + 3] += f.w;
                         }
-                        load_rf(c + CH_STEP);
                     }
                     if (p.out_f32 != nullptr && row_valid) {
                         float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * (size_t)p.out_f32_ld + nacc0);
