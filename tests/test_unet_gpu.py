@@ -47,6 +47,28 @@ def test_plain_unet(env):
         assert e < TOL
 
 
+def test_fp32_trunk_twins(env):
+    """Opt-in fp32 master copy of the residual trunk (UNetRunner.trunk_f32): the residual GEMMs read / write fp32 twins.
+    Same bound as the default path on the tiny topology (the gain shows at SDXL depth: config 2 final latents 1.53e-3 ->
+    1.17e-3, profiles/r02_parity_fullwidth_trunk_f32.jsonl), and the twins are really used (results differ bitwise)."""
+    from omg_b200.unet import UNetRunner
+    from oracle import unet as ou
+    cfg = env["cfg"]
+    B, H, W = 2, 32, 32
+    x, ctx, pooled, tid = _inputs(cfg, B, H, W, 1)
+    outs = []
+    for twin in (False, True):
+        r = UNetRunner(env["model"], B, H, W, use_graphs=False)
+        r.trunk_f32 = twin
+        r.set_conditioning([501.0], ctx, pooled, tid)
+        r.sample_in.copy_(to_nhwc8(x))
+        outs.append(from_nhwc(r.forward(0)))
+    ref = ou.unet_forward(ou.Ctx(env["sd"], ocfg(cfg)), x, 501.0, ctx, pooled, tid)
+    e0, e1 = rel(outs[0], ref), rel(outs[1], ref)
+    print("fp16 trunk rel err", e0, "fp32 twins rel err", e1)
+    assert e0 < TOL and e1 < TOL and not torch.equal(outs[0], outs[1])
+
+
 def test_graph_replay_matches_eager(env):
     from omg_b200.unet import UNetRunner
     cfg = env["cfg"]
