@@ -641,291 +641,6 @@ __global__ void __launch_bounds__(256, 2) attn_p_kernel(const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Two-stream variant (self-attention): the softmax at head_dim 64 is bound by instruction latency, not by a pipe - with
-// one softmax warpgroup per tile and two CTAs per SM every scheduler holds only two softmax warps, and ncu shows the
-// issue slots 50 % busy with "wait" (fixed-latency dependency) as the top stall.  Here every 128-query tile runs TWO
-// independent online-softmax streams - warpgroup 1 owns the even KV blocks, warpgroup 2 the odd ones, each with its own
-// running (m, l) and its own accumulator O_s in tensor memory - so an SM holds 4 softmax warps per scheduler (2 CTAs x
-// 2 streams).  The streams never synchronise inside the loop; they are merged once in the epilogue
-// (out = (O_0 2^(m_0-m) + O_1 2^(m_1-m)) / (l_0 2^(m_0-m) + l_1 2^(m_1-m))).
-// TMEM (256 columns): S_0 | S_1 | O_0 | O_1, 64 columns each; P_s (fp16 pairs, 32 columns) overwrites S_s in place -
-// the next Q.K^T of the stream is issued behind the P.V that reads it, and tcgen05.mma executes in issue order.
-// Per stream the chain is strictly serial (QK(j) -> softmax(j) -> PV(j) -> QK(j+2)); the four chains of an SM interleave.
-// The scores are read from TMEM twice (row maximum, then exponentials) so that a softmax thread needs ~70 live registers:
-// 2 CTAs x 384 threads leave 104 registers per softmax thread.
-struct Att2Cfg {
-    static constexpr int THREADS = 384;
-    static constexpr int KV_STAGES = 5;
-    static constexpr int SMEM = 1024 + ATT_Q_BYTES + KV_STAGES * 2 * ATT_K_BYTES + 512 + 2 * 128 * 8;
-    static constexpr int TMEM_COLS = 256;
-    static constexpr int S_COL0 = 0, O_COL0 = 128;
-};
-
-__global__ void __launch_bounds__(Att2Cfg::THREADS, 2) attn2_tc_kernel(const __grid_constant__ AttnParams p) {
-    using Cfg = Att2Cfg;
-    constexpr int KVS = Cfg::KV_STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* q_smem = smem;
-    uint8_t* kv_smem = q_smem + ATT_Q_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + KVS * 2 * ATT_K_BYTES);
-    uint64_t* q_full = bars;                 // 1
-    uint64_t* kv_full = bars + 1;            // KVS
-    uint64_t* kv_empty = kv_full + KVS;      // KVS
-    uint64_t* s_full = kv_empty + KVS;       // [stream]
-    uint64_t* p_full = s_full + 2;           // [stream]
-    uint64_t* o_final = p_full + 2;          // [stream]: every P.V of the stream has completed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
-    float2* ml_x = reinterpret_cast<float2*>(bars + 64);  // [stream][128 rows] (m, l) exchange for the merge
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int slab = blockIdx.x, head = blockIdx.y, item = blockIdx.z;
-    const int nkv = (p.n_kv + ATT_BKV - 1) / ATT_BKV;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&p.q_map);
-        tma_prefetch_desc(&p.k_map);
-        tma_prefetch_desc(&p.v_map);
-        mbar_init(q_full, 1);
-        for (int i = 0; i < KVS; ++i) {
-            mbar_init(&kv_full[i], 1);
-            mbar_init(&kv_empty[i], 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1);
-            mbar_init(&p_full[i], 4);
-            mbar_init(&o_final[i], 1);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    griddep_launch_dependents();
-    griddep_wait();
-    if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-        if (warp == 0) {
-            if (lane == 0) {  // ------------------------------------------------------------ TMA producer
-                mbar_arrive_expect_tx(q_full, ATT_Q_BYTES);
-                tma_load_3d(q_smem, &p.q_map, q_full, p.q_col0 + head * ATT_D, slab * ATT_BQ, p.q_b[item]);
-                int stage = 0;
-                uint32_t phase = 0;
-                const int kb = p.k_b[item], vb = p.v_b[item];
-                for (int j = 0; j < nkv; ++j) {
-                    mbar_wait(&kv_empty[stage], phase ^ 1);
-                    uint8_t* kd = kv_smem + stage * 2 * ATT_K_BYTES;
-                    mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_K_BYTES);
-                    tma_load_3d(kd, &p.k_map, &kv_full[stage], p.k_col0 + head * ATT_D, j * ATT_BKV, kb);
-                    tma_load_3d(kd + ATT_K_BYTES, &p.v_map, &kv_full[stage], p.v_col0 + head * ATT_D, j * ATT_BKV, vb);
-                    if (++stage == KVS) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-            }
-        } else if (warp <= 2) {
-            // ------------------------------------------------------------ MMA issuers: warp 1 -> stream 0, warp 2 -> stream 1
-            // (one issuing thread for both streams would wait for their P buffers in block order and lock the two
-            // chains together; with an issuer each, one stream's MMA round trip overlaps the other's softmax)
-            if (lane == 0) {
-                const int s = warp - 1;
-                constexpr uint32_t idesc_s = umma_idesc_f16(128, ATT_BKV, false, false);
-                constexpr uint32_t idesc_o = umma_idesc_f16(128, ATT_D, false, true);
-                const uint64_t q_desc = umma_desc_sw128(smem_u32(q_smem), 1024, 16);
-                const uint64_t k_desc0 = umma_desc_sw128(smem_u32(kv_smem), 1024, 16);
-                const uint64_t v_desc0 = umma_desc_sw128(smem_u32(kv_smem + ATT_K_BYTES), 1024, 1024);
-                const uint32_t s_col = tmem_base + Cfg::S_COL0 + s * 64, o_col = tmem_base + Cfg::O_COL0 + s * 64;
-                auto issue_s = [&](int jb) {
-                    const uint64_t kd = k_desc0 + (uint64_t)((jb % KVS) * ((2 * ATT_K_BYTES) >> 4));
-#pragma unroll
-                    for (int k = 0; k < ATT_D / 16; ++k) tc_mma_f16_ss(s_col, q_desc + 2 * k, kd + 2 * k, idesc_s, k > 0);
-                    tc_commit(&s_full[s]);
-                };
-                auto wait_kv = [&](int jb) { mbar_wait(&kv_full[jb % KVS], (jb / KVS) & 1); };
-                mbar_wait(q_full, 0);
-                if (s < nkv) {
-                    wait_kv(s);
-                    tc_fence_after();
-                    issue_s(s);
-                }
-                for (int j = s, i = 0; j < nkv; j += 2, ++i) {
-                    mbar_wait(&p_full[s], i & 1);  // P_s(j) is in TMEM (over S_s)
-                    tc_fence_after();
-                    const uint64_t vd = v_desc0 + (uint64_t)((j % KVS) * ((2 * ATT_K_BYTES) >> 4));
-#pragma unroll
-                    for (int k = 0; k < ATT_BKV / 16; ++k)
-                        tc_mma_f16_ts(o_col, s_col + 8 * k, vd + 128 * k, idesc_o, (i > 0 || k > 0) ? 1u : 0u);
-                    tc_commit(&kv_empty[j % KVS]);  // K_j and V_j belong to this stream alone
-                    if (j + 2 < nkv) {  // behind the P.V in issue order: S_s may be overwritten
-                        wait_kv(j + 2);
-                        tc_fence_after();
-                        issue_s(j + 2);
-                    } else {
-                        tc_commit(&o_final[s]);
-                    }
-                }
-            }
-        }
-    } else {
-        // ---------------------------------------------------------------------------------- softmax streams
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-        const int s = (warp - 4) >> 2;  // stream: KV blocks j = 2 i + s
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        const uint32_t s_tmem = tmem_base + Cfg::S_COL0 + s * 64 + lane_base;
-        const uint32_t o_tmem = tmem_base + Cfg::O_COL0 + s * 64 + lane_base;
-        const int n_s = (nkv - s + 1) >> 1;  // blocks of this stream
-        float m = -INFINITY, l = 0.f;
-        constexpr float kRescaleThreshold = 8.0f;
-        const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2);
-
-        for (int i = 0; i < n_s; ++i) {
-            const int j = 2 * i + s;
-            mbar_wait(&s_full[s], i & 1);  // S_s(j) is complete; so is P.V(j-2): O_s is quiescent until p_full below
-            tc_fence_after();
-            const int kv_left = p.n_kv - j * ATT_BKV;
-            // ---- pass A: row maximum
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t sr[32];
-                tmem_ld_32x32(s_tmem + c * 32, sr);
-                tc_wait_ld();
-                if (kv_left < ATT_BKV) {
-#pragma unroll
-                    for (int t = 0; t < 32; ++t)
-                        if (c * 32 + t >= kv_left) sr[t] = __float_as_uint(-INFINITY);
-                }
-#pragma unroll
-                for (int t = 0; t < 32; t += 8) {  // four independent chains
-                    mx0 = fmax3(mx0, __uint_as_float(sr[t]), __uint_as_float(sr[t + 1]));
-                    mx1 = fmax3(mx1, __uint_as_float(sr[t + 2]), __uint_as_float(sr[t + 3]));
-                    mx2 = fmax3(mx2, __uint_as_float(sr[t + 4]), __uint_as_float(sr[t + 5]));
-                    mx3 = fmax3(mx3, __uint_as_float(sr[t + 6]), __uint_as_float(sr[t + 7]));
-                }
-            }
-            const float m_cand = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2);
-            if (i == 0) {
-                m = m_cand;
-            } else {
-                const bool need = (m_cand - m) > kRescaleThreshold;
-                if (__any_sync(0xffffffffu, need)) {
-                    const float corr = need ? fast_exp2(m - m_cand) : 1.0f;
-                    if (need) m = m_cand;
-                    l *= corr;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t r[32];
-                        tmem_ld_32x32(o_tmem + c * 32, r);
-                        tc_wait_ld();
-#pragma unroll
-                        for (int t = 0; t < 32; ++t) r[t] = __float_as_uint(__uint_as_float(r[t]) * corr);
-                        tmem_st_32x32(o_tmem + c * 32, r);
-                    }
-                }
-            }
-            // ---- pass B: probabilities, written over the scores (columns 16 c .. 16 c + 15 <- keys 32 c .. 32 c + 31)
-            const uint64_t negm2 = pack_f32x2(-m, -m);
-            uint64_t sum2a = pack_f32x2(0.f, 0.f), sum2b = pack_f32x2(0.f, 0.f);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t sr[32];
-                tmem_ld_32x32(s_tmem + c * 32, sr);
-                tc_wait_ld();
-                uint32_t pk[16];
-#pragma unroll
-                for (int t = 0; t < 16; ++t) {
-                    const uint64_t x2 = ffma2(pack_f32x2(__uint_as_float(sr[2 * t]), __uint_as_float(sr[2 * t + 1])), scale2, negm2);
-                    float x0, x1, p0, p1;
-                    unpack_f32x2(x2, x0, x1);
-                    if ((OMG_ATT_POLY_MASK >> t) & 1) {
-                        poly_exp2_x2(x0, x1, p0, p1);
-                    } else {
-                        p0 = fast_exp2(x0);
-                        p1 = fast_exp2(x1);
-                    }
-                    if (kv_left < ATT_BKV) {  // keys beyond n_kv (zero-filled K rows) contribute nothing
-                        if (c * 32 + 2 * t >= kv_left) p0 = 0.f;
-                        if (c * 32 + 2 * t + 1 >= kv_left) p1 = 0.f;
-                    }
-                    if (t & 1) sum2b = fadd2(sum2b, pack_f32x2(p0, p1));
-                    else sum2a = fadd2(sum2a, pack_f32x2(p0, p1));
-                    pk[t] = pack_half2(p0, p1);
-                }
-                tmem_st_32x16(s_tmem + c * 16, pk);
-            }
-            float sa, sb;
-            unpack_f32x2(fadd2(sum2a, sum2b), sa, sb);
-            l += sa + sb;
-            tc_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[s]);
-        }
-        if (n_s > 0) {
-            mbar_wait(&o_final[s], 0);
-            tc_fence_after();
-        }
-        ml_x[s * 128 + row] = make_float2(m, l);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        // ---- merge: this warpgroup finalises output columns [32 s, 32 s + 32) from BOTH streams' accumulators
-        const float2 ml0 = ml_x[row], ml1 = ml_x[128 + row];
-        const float mm = fmaxf(ml0.x, ml1.x);
-        const float a0 = fast_exp2(ml0.x - mm);                        // stream 0 always has a block
-        const float a1 = nkv > 1 ? fast_exp2(ml1.x - mm) : 0.f;
-        const float inv = p.out_weight / (ml0.y * a0 + ml1.y * a1);
-        float o[32];
-        {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + Cfg::O_COL0 + lane_base + s * 32, r);
-            tc_wait_ld();
-#pragma unroll
-            for (int t = 0; t < 32; ++t) o[t] = __uint_as_float(r[t]) * (a0 * inv);
-            if (nkv > 1) {
-                tmem_ld_32x32(tmem_base + Cfg::O_COL0 + 64 + lane_base + s * 32, r);
-                tc_wait_ld();
-#pragma unroll
-                for (int t = 0; t < 32; ++t) o[t] = fmaf(__uint_as_float(r[t]), a1 * inv, o[t]);
-            }
-        }
-        const int qrow = slab * ATT_BQ + row;
-        if (qrow < p.n_q) {
-            __half* op = p.out + (long long)p.out_b[item] * p.out_bs + (long long)qrow * p.out_ld + p.out_col0 +
-                         head * ATT_D + s * 32;
-            uint4* op4 = reinterpret_cast<uint4*>(op);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                float v[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = o[t * 8 + e];
-                if (p.accumulate) {
-                    const uint4 u = op4[t];
-                    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 f = __half22float2(h2[e]);
-                        v[2 * e] += f.x;
-                        v[2 * e + 1] += f.y;
-                    }
-                }
-                op4[t] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
-                                    pack_half2(v[6], v[7]));
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------------
 // Cross-attention (77 text keys, 16 IP-adapter keys, <= 128 keys in general): the whole key sequence is ONE block, so a
 // head needs one Q.K^T, one softmax and one P.V.  Launched as one CTA per (query tile, head) - 640 CTAs of ~3 us at
 // N = 1024 - the old kernel spent most of its time in per-CTA setup (barrier init, TMEM allocation, pipeline fill):
@@ -1199,7 +914,6 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
               "omg_attention: output must be 16 B aligned per row");
     static bool configured = false;
     static int force_g = 0;
-    static int two_stream_min_kv = 1 << 30;
     static bool cross_kernel = true;
     static bool persistent = true;
     static int p_stages = 0;
@@ -1208,7 +922,6 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
         OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1, 3>::SMEM));
         OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1, 5>::SMEM));
         OMG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<2, 6>::SMEM));
-        OMG_CUDA(cudaFuncSetAttribute(attn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Att2Cfg::SMEM));
         OMG_CUDA(cudaFuncSetAttribute(attn_p_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttPCfg<5, 2>::SMEM));
         OMG_CUDA(cudaFuncSetAttribute(attn_p_kernel<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttPCfg<6, 1>::SMEM));
         const char* e7 = getenv("OMG_ATTN_PSTAGES");  // 5 | 6: force the (KV stages, Q buffers) = (5, 2) | (6, 1) variant
@@ -1224,10 +937,6 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
         force_g = e ? atoi(e) : 0;
         const char* e3 = getenv("OMG_ATTN_CROSS");  // 0: cross-attention through the per-(tile, head) kernel
         cross_kernel = !(e3 && atoi(e3) == 0);
-        // OMG_ATTN_STREAMS=2: self-attention through the two-stream kernel (measured slower than the single-stream kernel
-        // with double-buffered scores: 526-550 vs 610 TFLOP/s at N = 4096, 338-355 vs 396 at N = 1024; kept for measurements)
-        const char* e2 = getenv("OMG_ATTN_STREAMS");
-        two_stream_min_kv = (e2 && atoi(e2) == 2) ? 2 * ATT_BKV + 1 : (1 << 30);
         configured = true;
     }
     AttnParams p;
@@ -1274,7 +983,7 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
         if (d->n_kv <= 80) return launch_cross<80>(p, d, stream, max_qb, max_kb, max_vb);
         return launch_cross<128>(p, d, stream, max_qb, max_kb, max_vb);
     }
-    if (!force_g && persistent && d->n_kv > 2 * ATT_BKV && d->n_kv < two_stream_min_kv) {
+    if (!force_g && persistent && d->n_kv > 2 * ATT_BKV) {
         const int n_slabs = (d->n_q + ATT_BQ - 1) / ATT_BQ;
         const int n_tiles = n_slabs * d->heads * d->n_items;
         const int grid = std::min(n_tiles, 2 * num_sms);
@@ -1284,11 +993,6 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
         else
             OMG_CUDA(launch_pdl(attn_p_kernel<5, 2>, dim3(grid), dim3(256), AttPCfg<5, 2>::SMEM, stream, p, n_tiles, n_slabs));
         return check_launch("attn_p_kernel");
-    }
-    if (!force_g && d->n_kv >= two_stream_min_kv) {
-        dim3 grid((d->n_q + ATT_BQ - 1) / ATT_BQ, d->heads, d->n_items);
-        OMG_CUDA(launch_pdl(attn2_tc_kernel, grid, dim3(Att2Cfg::THREADS), Att2Cfg::SMEM, stream, p));
-        return check_launch("attn2_tc_kernel");
     }
     if (tiles == 1) {
         dim3 grid((d->n_q + ATT_BQ - 1) / ATT_BQ, d->heads, d->n_items);

@@ -158,8 +158,7 @@ def test_self_attention(ops, B, N, heads):
                                             (384, 1024, 3.0)])
 def test_attention_block_edges(ops, n_q, n_kv, gain):
     """Self-attention kernel edges: odd block counts, a partial last block, n_q != n_kv, and score ranges large enough
-    that the lazy O rescale fires; with and without `accumulate`.  (Run with OMG_ATTN_STREAMS=2 it covers the
-    two-stream variant: even / odd KV blocks merged in the epilogue.)"""
+    that the lazy O rescale fires; with and without `accumulate`."""
     heads = 3
     Cc = heads * 64
     q = rnd(2, n_q, Cc, seed=11) * gain
