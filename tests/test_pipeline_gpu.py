@@ -254,3 +254,96 @@ def test_callback_on_step_end_sees_and_may_replace_latents():
                    **kw).images
     wl.controller.reset()
     assert rel(out3, out) > 1e-2
+
+
+def test_main_pass_controlnet_condition_change_with_graphs():
+    """The LoRA pipeline with a spatial ControlNet on the main pass (lora_pipeline.py:519-540), called twice with two
+    different condition images through CUDA graphs: the captured ControlNet graph reads the condition embedding from a
+    persistent buffer, so the second call must see the new image (advisor finding of round 1) - each call is compared with
+    a fresh eager pipeline on the same image and with the oracle."""
+    from omg_b200.config import UNetConfig
+    from omg_b200.pipelines import ConceptModels, LoraMultiConceptPipeline
+    from omg_b200.unet import PackedUNet
+    from oracle import unet as ou
+    from oracle.pipeline import Concept, denoise
+    cfg = UNetConfig.tiny()
+    sd, csd = weights(cfg, 0), weights(cfg, 21, controlnet=True)
+    size, steps = 128, 4
+    g = torch.Generator().manual_seed(5)
+    lat0 = torch.randn(1, 4, size // 8, size // 8, generator=g).half()
+    conds = [r16(torch.rand(3, size, size, generator=g)) for _ in range(2)]
+    regions = [("x", "y"), ("z", "w")]
+    common = dict(prompt=[["p"] * 2, regions], negative_prompt=["n"] * 2, guidance_scale=5.0, num_inference_steps=steps,
+                  cross_attention_kwargs={"scale": 0.8}, lora_list=[], styleL=False, stage=1, height=size, width=size,
+                  output_type="latent", latents=lat0, controlnet_conditioning_scale=0.7)
+
+    def build(use_graphs):
+        unet = PackedUNet(cfg, sd)
+        pipe = LoraMultiConceptPipeline(unet, controlnet=PackedUNet(cfg, csd, controlnet=True), use_graphs=use_graphs)
+        return pipe, ConceptModels(unet)
+
+    pipe, cm = build(True)
+    outs = [pipe(image=[c, c], concept_models=cm, **common).images.clone() for c in conds]
+    outs.append(pipe(image=[conds[0], conds[0]], concept_models=cm, **common).images.clone())   # back to the first image
+    assert torch.equal(outs[0], outs[2]) and not torch.equal(outs[0], outs[1])
+    pe, ne, pp, np_ = pipe.encode_prompt(["p"] * 2, ["n"] * 2)
+    tid = torch.tensor([[size, size, 0, 0, size, size]], dtype=torch.float32)
+    for k, c in enumerate(conds):
+        eager, cm2 = build(False)
+        ref_eager = eager(image=[c, c], concept_models=cm2, **common).images
+        assert rel(outs[k], ref_eager) < 1e-5
+        ref = denoise(ou.Ctx(sd, ocfg(cfg)), lat0.float(), r16(torch.cat([ne, pe])), r16(torch.cat([np_, pp])), tid.repeat(4, 1),
+                      [], 1, steps, 5.0, controlnet=ou.Ctx(csd, ocfg(cfg)), controlnet_cond=c[None].repeat(4, 1, 1, 1),
+                      controlnet_scale=0.7)
+        e = rel(outs[k], ref)
+        print("main-pass controlnet pipeline rel err", e)
+        assert e < 2.5e-3
+
+
+def test_instantid_main_pass_controlnet_together_with_identitynet():
+    """InstantID with BOTH a spatial ControlNet on the main pass (controlnet2, instantid_pipeline.py:574-616) and the
+    IdentityNet on the concept pass (:639-674) while the concept UNet shares the packed base weights: one grouped forward
+    with two residual slots (rows 0-3 <- controlnet2, concept rows <- IdentityNet)."""
+    from omg_b200 import synthetic
+    from omg_b200.config import UNetConfig
+    from omg_b200.pipelines import ConceptModels, InstantidMultiConceptPipeline
+    from omg_b200.unet import PackedUNet
+    from oracle import unet as ou
+    from oracle.pipeline import Concept, denoise
+    from oracle.resampler import resampler_forward
+    cfg = UNetConfig.tiny()
+    sd, idsd, c2sd = weights(cfg, 0), weights(cfg, 41, controlnet=True), weights(cfg, 42, controlnet=True)
+    size = 128
+    rs = torch.load(os.path.join(G, "resampler.pt"))
+    ipw = {k: (r16(a), r16(b)) for k, (a, b) in synthetic.make_ip_adapter(cfg, 31).items()}
+    pipe = InstantidMultiConceptPipeline(PackedUNet(cfg, sd), controlnet=PackedUNet(cfg, idsd, controlnet=True))
+    pipe.controlnet2 = PackedUNet(cfg, c2sd, controlnet=True)
+    cm = ConceptModels(pipe.unet)
+    cm.load_ip_adapter_instantid(rs["sd"], ipw, heads=rs["heads"], dim_head=rs["dim_head"], num_tokens=16)
+    cm.set_ip_adapter_scale(0.8)
+    g = torch.Generator().manual_seed(53)
+    lat0 = torch.randn(1, 4, size // 8, size // 8, generator=g).half()
+    faces = [torch.nn.functional.normalize(torch.randn(512, generator=g), dim=0) for _ in range(2)]
+    kps, pose = r16(torch.rand(3, size, size, generator=g)), r16(torch.rand(3, size, size, generator=g))
+    masks = list(_masks(size))
+    regions = [("a man", "bad", None), ("a woman", "bad", None)]
+    prompts = ["two people"] * 2
+    out = pipe(prompt=[prompts, regions], negative_prompt=["noisy"] * 2, guidance_scale=3.0, num_inference_steps=STEPS,
+               concept_models=cm, stage=2, region_masks=masks, image=kps, controlnet_conditioning_scale=0.8, t2i_image=pose,
+               t2i_controlnet_conditioning_scale=0.6, face_embeds=faces, height=size, width=size, output_type="latent",
+               latents=lat0).images
+    pe, ne, pp, np_ = pipe.encode_prompt(prompts, ["noisy"] * 2)
+    tid = torch.tensor([[size, size, 0, 0, size, size]], dtype=torch.float32)
+    concepts = []
+    for k, reg in enumerate(regions):
+        e, n_, p_, np2 = pipe.encode_prompt(reg[0], reg[1])
+        emb = faces[k].reshape(1, 1, 512)
+        tokens = resampler_forward(rs["sd"], torch.cat([torch.zeros_like(emb), emb]), rs["heads"], rs["dim_head"])
+        concepts.append(Concept(r16(torch.cat([n_, e])), r16(torch.cat([np2, p_])), tid.repeat(2, 1), masks[k],
+                                unet=ou.Ctx(sd, ocfg(cfg), ip_weights=ipw, ip_tokens=16, ip_scale=0.8), image_tokens=r16(tokens)))
+    ref = denoise(ou.Ctx(sd, ocfg(cfg)), lat0.float(), r16(torch.cat([ne, pe])), r16(torch.cat([np_, pp])), tid.repeat(4, 1), concepts,
+                  2, STEPS, 3.0, controlnet=ou.Ctx(c2sd, ocfg(cfg)), controlnet_cond=pose[None].repeat(4, 1, 1, 1), controlnet_scale=0.6,
+                  identitynet=ou.Ctx(idsd, ocfg(cfg)), identity_cond=kps[None].repeat(2, 1, 1, 1), identity_scale=0.8)
+    e = rel(out, ref)
+    print("instantid + main-pass controlnet pipeline rel err", e)
+    assert e < 2.5e-3
