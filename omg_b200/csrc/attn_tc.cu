@@ -885,6 +885,14 @@ static int launch_cross(AttnParams& p, const omg_attn_desc* d, cudaStream_t stre
     int hpc = 1;
     while (hpc < 8 && hpc * 2 <= d->heads && (long)tiles * ((d->heads + 2 * hpc - 1) / (2 * hpc)) >= 148) hpc *= 2;
     if (d->heads % 5 == 0 && hpc == 4 && (long)tiles * (d->heads / 5) >= 128) hpc = 5;  // 10 / 20 heads: 5 per CTA, no tail group
+    {
+        static int force_hpc = -1;
+        if (force_hpc < 0) {
+            const char* e = getenv("OMG_ATTN_HPC");  // heads per CTA of the cross-attention kernel (measurements)
+            force_hpc = e ? atoi(e) : 0;
+        }
+        if (force_hpc > 0) hpc = std::min(force_hpc, d->heads);
+    }
     dim3 grid((d->n_q + ATT_BQ - 1) / ATT_BQ, (d->heads + hpc - 1) / hpc, d->n_items);
     OMG_CUDA(launch_pdl(attn_cross_kernel<NK>, grid, dim3(256), AttXCfg<NK>::SMEM, stream, p, hpc));
     return check_launch("attn_cross_kernel");
