@@ -66,6 +66,7 @@ struct alignas(64) GemmParams {
     int w_group_rows;          // > 0: the weight matrix holds one [N, K] plane per row group (per-stream merged LoRA)
     // fp32 master copy of the residual trunk: the addend is read from / the result also written to fp32 twins, so the
     // chain h <- h + f(h) accumulates in fp32 while every GEMM / norm input stays the fp16 copy
+    int l2_prefetch, l2_ahead; // bit 0: weights, bit 1: activations are prefetched into L2 l2_ahead K blocks ahead of the ring
     int gelu_exact;            // 1: libdevice erff (FMA pipe only) instead of the two-MUFU form; set for short-K launches
     const float* residual_f32;
     long long residual_f32_ld;
@@ -198,9 +199,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     for (int g2 = 0; g2 + 1 < p.n_col_groups; ++g2)
                         if (tile_pix0 >= p.col_group_end[g2]) n0 += p.w_group_rows;
                 }
+                // L2 prefetch cursor: runs p.l2_prefetch K blocks ahead of the shared-memory loads of this tile (weights
+                // stream from DRAM once per launch: without it a DRAM miss stalls a 4-stage ring that only covers an
+                // L2-hit latency)
+                int ps = 0, pkb = 0;
+                auto prefetch_next = [&]() {
+                    if (ps >= p.n_segs) return;
+                    const SegDev pg = p.segs[ps];
+                    if (p.l2_prefetch & 1) {
+                        tma_prefetch_2d(&p.b_maps[pg.b_map], pg.b_k0 + pkb * BK, n0);
+                        if constexpr (BN > 256) tma_prefetch_2d(&p.b_maps[pg.b_map], pg.b_k0 + pkb * BK, n0 + 160);
+                    }
+                    if (p.l2_prefetch & 2) {
+                        tma_prefetch_4d(&p.a_maps[pg.a_map], pg.a_c0 + pkb * BK, w0 + pg.dx, h0 + pg.dy, b);
+                        if constexpr (MT == 2) tma_prefetch_4d(&p.a_maps[pg.a_map], pg.a_c0 + pkb * BK, w1 + pg.dx, h1 + pg.dy, b1);
+                    }
+                    if (++pkb == pg.k_blocks) {
+                        pkb = 0;
+                        ++ps;
+                    }
+                };
+                if (p.l2_prefetch) {
+                    // skip what the ring will load right away (STAGES blocks), then request the next L2_AHEAD blocks
+                    for (int i = 0; i < STAGES && ps < p.n_segs; ++i) {
+                        if (++pkb == p.segs[ps].k_blocks) {
+                            pkb = 0;
+                            ++ps;
+                        }
+                    }
+                    for (int i = 0; i < p.l2_ahead; ++i) prefetch_next();
+                }
                 for (int s = 0; s < p.n_segs; ++s) {
                     const SegDev sg = p.segs[s];
                     for (int kb = 0; kb < sg.k_blocks; ++kb) {
+                        if (p.l2_prefetch) prefetch_next();
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
                         uint8_t* b_dst = a_dst + Cfg::A_BYTES;
@@ -780,6 +812,17 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     OMG_CHECK(!p.stats_in || (p.col_c1 && p.col_c2 && d->ln_dim > 0 && d->row_stats_parts >= 1 && !d->rowvec),
               "omg_gemm: folded LayerNorm needs col_c1, col_c2, ln_dim, row_stats_parts and no rowvec");
     OMG_CHECK(!p.stats_out || !geglu, "omg_gemm: row statistics cannot be emitted by the GEGLU epilogue");
+    {
+        static int pf = -1, ahead = 6;
+        if (pf < 0) {
+            const char* e = getenv("OMG_GEMM_L2PF");  // 0 off | 1 weights | 2 activations | 3 both
+            pf = e ? atoi(e) : 0;
+            const char* e2 = getenv("OMG_GEMM_L2PF_AHEAD");
+            if (e2) ahead = atoi(e2);
+        }
+        p.l2_prefetch = pf;
+        p.l2_ahead = ahead;
+    }
     p.residual_f32 = static_cast<const float*>(d->residual_f32);
     p.residual_f32_ld = d->residual_f32_ld;
     p.out_f32 = static_cast<float*>(d->out_f32);
