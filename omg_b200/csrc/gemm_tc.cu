@@ -66,8 +66,6 @@ struct alignas(64) GemmParams {
     int w_group_rows;          // > 0: the weight matrix holds one [N, K] plane per row group (per-stream merged LoRA)
     // fp32 master copy of the residual trunk: the addend is read from / the result also written to fp32 twins, so the
     // chain h <- h + f(h) accumulates in fp32 while every GEMM / norm input stays the fp16 copy
-    int l2_prefetch, l2_ahead; // bit 0: weights, bit 1: activations are prefetched into L2 l2_ahead K blocks ahead of the ring
-    int gelu_exact;            // 1: libdevice erff (FMA pipe only) instead of the two-MUFU form; set for short-K launches
     const float* residual_f32;
     long long residual_f32_ld;
     float* out_f32;
@@ -105,25 +103,20 @@ struct GemmCfg {
     static constexpr int ACC_STAGES = (MT == 2 || BN > 256) ? 1 : 2;  // MT = 2: the two accumulators ARE the two sub-tiles
 };
 
-// erf-GELU with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the fp16 output rounding): branch-free,
-// two MUFU ops (rcp, ex2) + ~10 FMA-pipe instructions; erff() is ~30 instructions with a branch, and the GEGLU epilogue
-// evaluates it 32 K times per 128 x 256 tile (ncu: issue slots 38 % busy in the FF1 kernel, the lowest SM clock of all
-// kernels under the power cap).
-__device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752f;
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));  // MUFU.RCP (1 ulp); __frcp_rn is a slow exact sequence
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float e = fast_exp2(-1.4426950408889634f * z * z);
-    const float erf_abs = fmaf(-poly * t, e, 1.0f);          // erf(|x| / sqrt 2)
-    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
-}
+// GEGLU / erf-GELU use libdevice's erff: measured on one box against a branch-free Abramowitz-Stegun form (rcp + ex2 on the
+// MUFU): 91 vs 94-98 us on FF1 4096 x 10240 x 1280 and 109-112 vs 147-157 us on 16384 x 5120 x 640 (the epilogue of a short-K
+// tile is MUFU-bound with the two-transcendental form), so erff stays.
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-template <int BN, int EPI, int CTAS, int MT>
+// FEAT selects what the epilogue carries besides bias / time-embedding vector / residual / LayerNorm fold / row statistics:
+//   0  nothing else (the linears of the transformer blocks: the hot instantiations stay as lean as they were in round 1 -
+//      same-box A/B: the all-in-one epilogue cost +3..17 % on these launches, profiles/r02_gemm_builds_ab.jsonl)
+//   1  + GroupNorm column statistics (convs, proj_out)
+//   2  + activations (SiLU, quick-GELU, erf / tanh GELU) and the fp32 residual-trunk twins (once-per-call MLPs, CLIP / SAM
+//      towers, OMG_TRUNK_F32)
+template <int BN, int EPI, int CTAS, int MT, int FEAT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+    constexpr bool kStats = FEAT >= 1, kExtra = FEAT >= 2;
     static_assert(MT == 1 || CTAS == 1, "tall tiles are a single-CTA variant");
     static_assert(BN <= 256 || (CTAS == 2 && BN == 320 && EPI != OMG_EPI_GEGLU), "BN = 320 exists as a CTA-pair tile only");
     using Cfg = GemmCfg<BN, CTAS, MT>;
@@ -199,40 +192,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     for (int g2 = 0; g2 + 1 < p.n_col_groups; ++g2)
                         if (tile_pix0 >= p.col_group_end[g2]) n0 += p.w_group_rows;
                 }
-                // L2 prefetch cursor: runs p.l2_prefetch K blocks ahead of the shared-memory loads of this tile (weights
-                // stream from DRAM once per launch: without it a DRAM miss stalls a 4-stage ring that only covers an
-                // L2-hit latency)
-                int ps = 0, pkb = 0;
-                auto prefetch_next = [&]() {
-                    if (ps >= p.n_segs) return;
-                    const SegDev pg = p.segs[ps];
-                    if (p.l2_prefetch & 1) {
-                        tma_prefetch_2d(&p.b_maps[pg.b_map], pg.b_k0 + pkb * BK, n0);
-                        if constexpr (BN > 256) tma_prefetch_2d(&p.b_maps[pg.b_map], pg.b_k0 + pkb * BK, n0 + 160);
-                    }
-                    if (p.l2_prefetch & 2) {
-                        tma_prefetch_4d(&p.a_maps[pg.a_map], pg.a_c0 + pkb * BK, w0 + pg.dx, h0 + pg.dy, b);
-                        if constexpr (MT == 2) tma_prefetch_4d(&p.a_maps[pg.a_map], pg.a_c0 + pkb * BK, w1 + pg.dx, h1 + pg.dy, b1);
-                    }
-                    if (++pkb == pg.k_blocks) {
-                        pkb = 0;
-                        ++ps;
-                    }
-                };
-                if (p.l2_prefetch) {
-                    // skip what the ring will load right away (STAGES blocks), then request the next L2_AHEAD blocks
-                    for (int i = 0; i < STAGES && ps < p.n_segs; ++i) {
-                        if (++pkb == p.segs[ps].k_blocks) {
-                            pkb = 0;
-                            ++ps;
-                        }
-                    }
-                    for (int i = 0; i < p.l2_ahead; ++i) prefetch_next();
-                }
                 for (int s = 0; s < p.n_segs; ++s) {
                     const SegDev sg = p.segs[s];
                     for (int kb = 0; kb < sg.k_blocks; ++kb) {
-                        if (p.l2_prefetch) prefetch_next();
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
                         uint8_t* b_dst = a_dst + Cfg::A_BYTES;
@@ -438,7 +400,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                             a = __uint_as_float(r[i]) + sb[off + i];
                             g = __uint_as_float(r[i + 1]) + sb[off + i + 1];
                         }
-                        return a * (p.gelu_exact ? 0.5f * g * (1.0f + erff(g * 0.70710678118654752f)) : gelu_erf(g));
+                        return a * gelu_exact(g);
                     };
 #pragma unroll
                     for (int j = 0; j < 8; ++j)  // columns (4j, 4j+1) and (4j+2, 4j+3) are (value, gate) pairs
@@ -460,20 +422,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sb[j];
                     }
-                    if (p.act_silu == 1) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
-                    } else if (p.act_silu == 2) {  // quick_gelu
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-1.702f * v[j]));
-                    } else if (p.act_silu == 3) {  // erf-gelu
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-                    } else if (p.act_silu == 4) {  // tanh-gelu (EfficientViT-SAM): 0.5 x (1 + tanh(sqrt(2/pi)(x + 0.044715 x^3)))
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float u = 0.7978845608028654f * fmaf(0.044715f * v[j] * v[j], v[j], v[j]);
-                            v[j] = 0.5f * v[j] * (2.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * u)));
+                    if constexpr (kExtra) {
+                        if (p.act_silu == 1) {
+    #pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
+                        } else if (p.act_silu == 2) {  // quick_gelu
+    #pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-1.702f * v[j]));
+                        } else if (p.act_silu == 3) {  // erf-gelu
+    #pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = gelu_exact(v[j]);
+                        } else if (p.act_silu == 4) {  // tanh-gelu (EfficientViT-SAM): 0.5 x (1 + tanh(sqrt(2/pi)(x + 0.044715 x^3)))
+    #pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float u = 0.7978845608028654f * fmaf(0.044715f * v[j] * v[j], v[j], v[j]);
+                                v[j] = 0.5f * v[j] * (2.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * u)));
+                            }
                         }
                     }
                     if (has_res) {
@@ -490,6 +454,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                         }
                         load_res(c + 2 * CH_STEP, resb);
                     }
+                    if constexpr (kExtra) {
                     if (p.residual_f32 != nullptr && row_valid) {  // fp32 addend (prefetching it a chunk ahead was measured: no gain)
                         const float4* rp = reinterpret_cast<const float4*>(p.residual_f32 + pix * (size_t)p.residual_f32_ld + nacc0);
 #pragma unroll
@@ -505,6 +470,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                         float4* op = reinterpret_cast<float4*>(p.out_f32 + pix * (size_t)p.out_f32_ld + nacc0);
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                    }
                     }
                     if (p.stats_out != nullptr) {
                         if (nacc0 + 32 <= p.N) {
@@ -526,7 +492,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                     for (int j = 0; j < 16; ++j) outp[j] = pack_half2(v[2 * j], v[2 * j + 1]);
                 }
-                if constexpr (EPI != OMG_EPI_GEGLU) {
+                if constexpr (EPI != OMG_EPI_GEGLU && kStats) {
                     if (p.col_stats != nullptr && !row_valid) {  // rows outside the image count as zeros
 #pragma unroll
                         for (int j = 0; j < 16; ++j) outp[j] = 0u;
@@ -549,7 +515,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                     tma_store_4d(&p.d_map, sbuf, nout0, sw, sh, b);
                     tma_store_commit();
                 }
-                if constexpr (EPI != OMG_EPI_GEGLU) {
+                if constexpr (EPI != OMG_EPI_GEGLU && kStats) {
                     if (p.col_stats != nullptr && b < p.img_b) {
                         // per-channel (sum, sumsq) of the 32 rows x 32 channels just staged (the fp16-rounded values the
                         // consumer GroupNorm will see): lane = (row parity, channel pair); 16 conflict-free LDS.32
@@ -630,13 +596,13 @@ static int view_to_tmap(CUtensorMap* m, const omg_view4& v, uint32_t box_c, uint
     return make_tmap_f16(m, v.ptr, 4, dims, strides, box, sw);
 }
 
-template <int BN, int EPI, int CTAS, int MT = 1>
-static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+template <int BN, int EPI, int CTAS, int MT, int FEAT>
+static int launch_gemm_f(const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, CTAS, MT>;
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
-        OMG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, CTAS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        OMG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, CTAS, MT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::SMEM_BYTES));
         int dev = 0;
         OMG_CUDA(cudaGetDevice(&dev));
@@ -645,8 +611,20 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
     }
     const int units = ((p.m_tiles + CTAS * MT - 1) / (CTAS * MT)) * p.n_tiles;
     const int grid = CTAS * std::min(units, num_sms / CTAS);
-    OMG_CUDA(launch_cluster(gemm_tc_kernel<BN, EPI, CTAS, MT>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, CTAS, p));
+    OMG_CUDA(launch_cluster(gemm_tc_kernel<BN, EPI, CTAS, MT, FEAT>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, CTAS, p));
     return check_launch("gemm_tc_kernel");
+}
+
+// FEAT dispatch: 0 lean, 1 + GroupNorm column statistics, 2 + activations / fp32 twins (GEGLU launches are always lean)
+template <int BN, int EPI, int CTAS, int MT = 1>
+static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+    if constexpr (EPI == OMG_EPI_GEGLU) {
+        return launch_gemm_f<BN, EPI, CTAS, MT, 0>(p, stream);
+    } else {
+        if (p.act_silu != 0 || p.residual_f32 != nullptr || p.out_f32 != nullptr) return launch_gemm_f<BN, EPI, CTAS, MT, 2>(p, stream);
+        if (p.col_stats != nullptr) return launch_gemm_f<BN, EPI, CTAS, MT, 1>(p, stream);
+        return launch_gemm_f<BN, EPI, CTAS, MT, 0>(p, stream);
+    }
 }
 
 static bool use_tall_tiles(long m_tiles, long n_tiles, long k_blocks) {
@@ -812,17 +790,6 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     OMG_CHECK(!p.stats_in || (p.col_c1 && p.col_c2 && d->ln_dim > 0 && d->row_stats_parts >= 1 && !d->rowvec),
               "omg_gemm: folded LayerNorm needs col_c1, col_c2, ln_dim, row_stats_parts and no rowvec");
     OMG_CHECK(!p.stats_out || !geglu, "omg_gemm: row statistics cannot be emitted by the GEGLU epilogue");
-    {
-        static int pf = -1, ahead = 6;
-        if (pf < 0) {
-            const char* e = getenv("OMG_GEMM_L2PF");  // 0 off | 1 weights | 2 activations | 3 both
-            pf = e ? atoi(e) : 0;
-            const char* e2 = getenv("OMG_GEMM_L2PF_AHEAD");
-            if (e2) ahead = atoi(e2);
-        }
-        p.l2_prefetch = pf;
-        p.l2_ahead = ahead;
-    }
     p.residual_f32 = static_cast<const float*>(d->residual_f32);
     p.residual_f32_ld = d->residual_f32_ld;
     p.out_f32 = static_cast<float*>(d->out_f32);
@@ -884,10 +851,6 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
     // the TMA box of the weight tile is this CTA's slice: BN rows, or BN/2 for a CTA pair
     long k_blocks = 0;
     for (int i = 0; i < p.n_segs; ++i) k_blocks += p.segs[i].k_blocks;
-    // GEGLU epilogue: with K <= 960 the epilogue, not the mainloop, bounds the tile and the two MUFU ops per gate of
-    // gelu_erf (quarter-rate unit) cost more than erff's ~30 FMA-pipe instructions (measured, same box: 16384 x 5120 x 640
-    // 148 vs 159 us; 4096 x 10240 x 1280 the other way round: 98 vs 93 us)
-    p.gelu_exact = k_blocks < 16 ? 1 : 0;
     bool pair_ok = true;  // both CTAs of a pair must belong to the same stream
     for (int i = 0; i + 1 < p.n_col_groups; ++i) pair_ok = pair_ok && (p.col_group_end[i] % 256 == 0);
     // BN = 160 pairs are available on request but never chosen: measured 0..-8 % (profiles/r01_kernel_bench.json)
