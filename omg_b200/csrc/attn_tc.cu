@@ -503,10 +503,6 @@ __global__ void __launch_bounds__(256, 2) attn_p_kernel(const __grid_constant__ 
         }
     } else {
         // ---------------------------------------------------------------------------------- softmax group
-        // The scores are fetched from TMEM one KV block AHEAD of the exponentials: while block g's exp2 work (MUFU-bound)
-        // runs, S(g+1) is already on its way into registers and its row maximum - a dependent FMNMX chain that used to sit
-        // alone between the TMEM load and the first exponential (ncu source page, round 2: 10 % of the group's samples on
-        // 32 serial FMNMX3, 13 % waiting for s_full, 3 % on the load) - is interleaved with the second half of the block.
         asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         const int q = warp & 3;
         const int row = q * 32 + lane;
@@ -516,113 +512,90 @@ __global__ void __launch_bounds__(256, 2) attn_p_kernel(const __grid_constant__ 
         const uint32_t p_tmem = tmem_base + Cfg::P_COL0 + lane_base;
         constexpr float kRescaleThreshold = 8.0f;
         const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2);
-        int n_my = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ++n_my;
-        const uint32_t total = (uint32_t)n_my * (uint32_t)nkv;
         uint32_t g = 0;
-        int ti = 0, j = 0;
-        float m = -INFINITY, l = 0.f;
-
-        auto mask_half = [&](uint32_t(&s)[32], const int kv_left) {  // kv_left: keys left from this half's first column
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (i >= kv_left) s[i] = __float_as_uint(-INFINITY);
-        };
-        auto half_max = [&](const uint32_t(&s)[32], float(&mk)[4]) {  // four independent chains instead of one of depth 32
-#pragma unroll
-            for (int i = 0; i < 16; ++i) mk[i & 3] = fmax3(mk[i & 3], __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
-        };
-        // 16 score pairs of one 32-column half -> probabilities (fp16 pairs) + their sum
-        auto exp_half = [&](const uint32_t(&sc)[32], const uint64_t negm2, uint64_t& sum2, uint32_t(&pk)[16]) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const uint64_t x2 = ffma2(pack_f32x2(__uint_as_float(sc[2 * i]), __uint_as_float(sc[2 * i + 1])), scale2, negm2);
-                float x0, x1, p0, p1;
-                unpack_f32x2(x2, x0, x1);
-                if ((OMG_ATT_POLY_MASK >> i) & 1) {
-                    poly_exp2_x2(x0, x1, p0, p1);
-                } else {
-                    p0 = fast_exp2(x0);
-                    p1 = fast_exp2(x1);
-                }
-                sum2 = fadd2(sum2, pack_f32x2(p0, p1));
-                pk[i] = pack_half2(p0, p1);
-            }
-        };
-        // one KV block: (c0, c1) hold the two 32-column halves of S(g) (tail already masked) and `mx` its row maximum;
-        // S(g+1) goes to (n0, c0) - c0 is dead once its exponentials are done - so three 32-register blocks rotate
-        // through the roles (a fourth block would leave no registers for the loop state: LDTM.x32 wants aligned blocks)
-        float mx = 0.f;
-        auto step = [&](uint32_t(&c0)[32], uint32_t(&c1)[32], uint32_t(&n0)[32]) {
-            const int b = g & 1;
-            const bool has_next = g + 1 < total;
-            const int j_next = (j == nkv - 1) ? 0 : j + 1;
-            const float m_cand = fmaxf(j == 0 ? -INFINITY : m, mx * p.scale_log2);
-            if (j == 0) {
-                m = m_cand;
-                l = 0.f;
-            } else {
-                const bool need = (m_cand - m) > kRescaleThreshold;
-                if (__any_sync(0xffffffffu, need)) {
-                    // P.V of the previous block (same tile: j >= 1) must have landed before O is rescaled
-                    mbar_wait(&p_empty[b ^ 1], ((g - 1) >> 1) & 1);
-                    tc_fence_after();
-                    const float corr = need ? fast_exp2(m - m_cand) : 1.0f;
-                    if (need) m = m_cand;
-                    l *= corr;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t r[32];
-                        tmem_ld_32x32(o_tmem + c * 32, r);
-                        tc_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
-                        tmem_st_32x32(o_tmem + c * 32, r);
-                    }
-                    tc_wait_st();
-                }
-            }
-            // S(g+1): first half requested now, second half once cur[0] is dead (register budget: 200 per thread)
-            const uint32_t s_next = s_tmem + (b ^ 1) * 64;
-            const int kv_left_next = p.n_kv - j_next * ATT_BKV;
-            if (has_next) {
-                mbar_wait(&s_full[b ^ 1], ((g + 1) >> 1) & 1);
-                tc_fence_after();
-                tmem_ld_32x32(s_next, n0);
-            }
-            uint64_t sum2 = pack_f32x2(0.f, 0.f);
-            const uint64_t negm2 = pack_f32x2(-m, -m);
-            uint32_t pk0[16], pk1[16];
-            exp_half(c0, negm2, sum2, pk0);
-            if (g >= 2) mbar_wait(&p_empty[b], ((g >> 1) & 1) ^ 1);  // P[b] consumed by the P.V of running block g - 2
-            tmem_st_32x16(p_tmem + b * 32, pk0);
-            tc_wait_ld();  // n0 is in registers (no-op without a next block)
-            if (has_next) tmem_ld_32x32(s_next + 32, c0);
-            if (kv_left_next < 32) mask_half(n0, kv_left_next);
-            float mk[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            half_max(n0, mk);  // interleaves with the exponentials below
-            exp_half(c1, negm2, sum2, pk1);
-            tmem_st_32x16(p_tmem + b * 32 + 16, pk1);
-            float sum, sum_hi;
-            unpack_f32x2(sum2, sum, sum_hi);
-            l += sum + sum_hi;
-            tc_wait_ld();
-            if (kv_left_next < ATT_BKV) mask_half(c0, kv_left_next - 32);
-            half_max(c0, mk);
-            tc_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[b]);
-            mx = fmaxf(fmax3(mk[0], mk[1], mk[2]), mk[3]);
-            ++g;
-            if (++j < nkv) return;
-            // tile epilogue: O is complete once the last P.V has landed; read it out and hand TMEM back at once
-            j = 0;
-            const int tile = blockIdx.x + ti * (int)gridDim.x;
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
             const int slab = tile % n_slabs, head = (tile / n_slabs) % p.heads, item = tile / (n_slabs * p.heads);
+            float m = -INFINITY, l = 0.f;
+            for (int j = 0; j < nkv; ++j, ++g) {
+                const int b = g & 1;
+                mbar_wait(&s_full[b], (g >> 1) & 1);
+                tc_fence_after();
+                const int kv_left = p.n_kv - j * ATT_BKV;
+                uint32_t sr[2][32];
+                tmem_ld_32x32(s_tmem + b * 64, sr[0]);
+                tmem_ld_32x32(s_tmem + b * 64 + 32, sr[1]);
+                tc_wait_ld();
+                if (kv_left < ATT_BKV) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i >= kv_left) sr[c][i] = __float_as_uint(-INFINITY);
+                }
+                float mx = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
+                const float m_cand = fmaxf(m, mx * p.scale_log2);
+                if (j == 0) {
+                    m = m_cand;
+                } else {
+                    const bool need = (m_cand - m) > kRescaleThreshold;
+                    if (__any_sync(0xffffffffu, need)) {
+                        // P.V of the previous block (same tile: j >= 1) must have landed before O is rescaled
+                        mbar_wait(&p_empty[b ^ 1], ((g - 1) >> 1) & 1);
+                        tc_fence_after();
+                        const float corr = need ? fast_exp2(m - m_cand) : 1.0f;
+                        if (need) m = m_cand;
+                        l *= corr;
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t r[32];
+                            tmem_ld_32x32(o_tmem + c * 32, r);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+                            tmem_st_32x32(o_tmem + c * 32, r);
+                        }
+                        tc_wait_st();
+                    }
+                }
+                if (g >= 2) mbar_wait(&p_empty[b], ((g >> 1) & 1) ^ 1);  // P[b] consumed by the P.V of running block g - 2
+                uint64_t sum2 = pack_f32x2(0.f, 0.f);
+                const uint64_t negm2 = pack_f32x2(-m, -m);
+                uint32_t pk[32];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint64_t x2 = ffma2(pack_f32x2(__uint_as_float(sr[c][2 * i]), __uint_as_float(sr[c][2 * i + 1])),
+                                                  scale2, negm2);
+                        float x0, x1, p0, p1;
+                        unpack_f32x2(x2, x0, x1);
+                        if ((OMG_ATT_POLY_MASK >> i) & 1) {
+                            poly_exp2_x2(x0, x1, p0, p1);
+                        } else {
+                            p0 = fast_exp2(x0);
+                            p1 = fast_exp2(x1);
+                        }
+                        sum2 = fadd2(sum2, pack_f32x2(p0, p1));
+                        pk[c * 16 + i] = pack_half2(p0, p1);
+                    }
+                }
+                tmem_st_32x32(p_tmem + b * 32, pk);
+                float sum, sum_hi;
+                unpack_f32x2(sum2, sum, sum_hi);
+                l += sum + sum_hi;
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[b]);
+            }
+            // tile epilogue: O is complete once the last P.V has landed; read it out and hand TMEM back at once
             mbar_wait(o_done, ti & 1);
             tc_fence_after();
-            ++ti;
             float o_acc[ATT_D];
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -659,27 +632,6 @@ __global__ void __launch_bounds__(256, 2) attn_p_kernel(const __grid_constant__ 
                     op4[t] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
                                         pack_half2(v[6], v[7]));
                 }
-            }
-        };
-        if (total > 0) {
-            uint32_t x0[32], x1[32], x2[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x2[i] = 0u;
-            mbar_wait(&s_full[0], 0);
-            tc_fence_after();
-            tmem_ld_32x32(s_tmem, x0);
-            tmem_ld_32x32(s_tmem + 32, x1);
-            tc_wait_ld();
-            if (p.n_kv < 32) mask_half(x0, p.n_kv);
-            if (p.n_kv < ATT_BKV) mask_half(x1, p.n_kv - 32);
-            float mk0[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            half_max(x0, mk0);
-            half_max(x1, mk0);
-            mx = fmaxf(fmax3(mk0[0], mk0[1], mk0[2]), mk0[3]);
-            while (g < total) {
-                step(x0, x1, x2);                   // next block in (x2, x0)
-                if (g < total) step(x2, x0, x1);    // next block in (x1, x2)
-                if (g < total) step(x1, x2, x0);    // next block in (x0, x1)
             }
         }
     }

@@ -64,11 +64,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef OMG_MBAR_TIMEOUT_CYCLES
 #define OMG_MBAR_TIMEOUT_CYCLES (4000000000LL)
 #endif
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~`ns` have passed, instead
+// of coming back after the (short) system default - a polling producer / MMA-issuer warp otherwise issues a try_wait + branch
+// every ~80 ns next to the softmax / epilogue warps of its scheduler (ncu: 18 % of all instructions of the attention kernel)
+#ifndef OMG_MBAR_SUSPEND_NS
+#define OMG_MBAR_SUSPEND_NS 20000
+#endif
+__device__ __forceinline__ bool mbar_try_wait_long(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)OMG_MBAR_SUSPEND_NS)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait_long(bar, parity)) {
         if ((++spins & 0x3FF) == 0 && clock64() - t0 > OMG_MBAR_TIMEOUT_CYCLES) {
             printf("omg: mbarrier timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", (int)blockIdx.x,
                    (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x, smem_u32(bar), parity);
