@@ -237,6 +237,31 @@ int omg_group1x1(const void* x, const void* w, void* y, long long pixels, int C,
 int omg_relu_linear_attention(const void* qkv, void* out, int B, int N, int heads, int dim, float eps, void* stream);
 int omg_resize_bicubic(const void* x, void* y, int B, int H, int W, int C, int Ho, int Wo, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Launch plans: a forward as a handle.  The reference drives one UNet forward as a Python call
+ * (`self.unet(latent_model_input, t, ...)`, src/pipelines/lora_pipeline.py:558-567, 588-606); a host that is not Python -
+ * or does not want ~720 descriptor builds per forward - records that call once and replays it through this handle:
+ *
+ *   omg_plan* fwd = omg_plan_create();
+ *   omg_plan_record_begin(fwd);  ... one eager forward: omg_gemm / omg_attention / omg_groupnorm_apply / ... ;
+ *   omg_plan_record_end(fwd);
+ *   for every step:  (write the sample and the step's time embedding into their buffers)  omg_plan_run(fwd, stream);
+ *
+ * While a thread records, every entry point above that launched successfully also appends a copy of its call - the
+ * descriptor by value, so every pointer in it must stay valid for as long as the plan is run (the executor's persistent
+ * workspace does) - and omg_plan_run re-issues the calls in order on `stream` with no further host work than the launches.
+ * Replay validates and encodes the descriptors again, so a plan stays valid across processes' lifetimes of the buffers only.
+ * One recording per thread at a time; a plan may be run from any thread once recording has ended.
+ */
+typedef struct omg_plan omg_plan;
+omg_plan* omg_plan_create(void);
+void omg_plan_destroy(omg_plan* plan);
+int omg_plan_record_begin(omg_plan* plan);
+int omg_plan_record_end(omg_plan* plan);
+int omg_plan_length(const omg_plan* plan);     /* number of recorded launches; -1 for NULL */
+int omg_plan_clear(omg_plan* plan);
+int omg_plan_run(const omg_plan* plan, void* stream);
+
 /* Error string of the last failing call on this thread (never NULL). */
 const char* omg_last_error(void);
 /* Library / build identification: returns e.g. "omg_b200 sm_100a". */

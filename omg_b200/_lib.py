@@ -79,6 +79,13 @@ SYMBOLS = {
     "omg_group1x1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "omg_relu_linear_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "omg_resize_bicubic": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "omg_plan_create": (C.c_void_p, []),
+    "omg_plan_destroy": (None, [C.c_void_p]),
+    "omg_plan_record_begin": (C.c_int, [C.c_void_p]),
+    "omg_plan_record_end": (C.c_int, [C.c_void_p]),
+    "omg_plan_length": (C.c_int, [C.c_void_p]),
+    "omg_plan_clear": (C.c_int, [C.c_void_p]),
+    "omg_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "omg_last_error": (C.c_char_p, []),
     "omg_version": (C.c_char_p, []),
     "omg_launch_count": (C.c_uint64, []),

@@ -910,7 +910,7 @@ static int make_attn_map(CUtensorMap* m, const void* ptr, int cols, int ld, int 
 
 using namespace omg;
 
-extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
+static int attention_impl(const omg_attn_desc* d, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     OMG_CHECK(d != nullptr, "omg_attention: null descriptor");
     OMG_CHECK(d->head_dim == 64, "omg_attention: head_dim %d unsupported (SDXL uses 64)", d->head_dim);
@@ -1013,4 +1013,14 @@ extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
         OMG_CUDA(launch_pdl(attn_tc_kernel<2, 6>, grid, dim3(AttCfg<2, 6>::THREADS), AttCfg<2, 6>::SMEM, stream, p));
     }
     return check_launch("attn_tc_kernel");
+}
+
+// C-ABI entry points: launch, and - while this thread records a launch plan (omg_plan_record_begin) - remember the call
+extern "C" int omg_attention(const omg_attn_desc* d, void* stream_) {
+    const int rc = attention_impl(d, stream_);
+    if (rc == 0 && ::omg::plan_recording()) {
+        const omg_attn_desc c = *d;  // by value: a plan outlives the caller's descriptor
+        ::omg::plan_note([c](void* s) { return attention_impl(&c, s); });
+    }
+    return rc;
 }

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(SM_THREADS) softmax_rows_kernel(__half* __rest
 
 using namespace omg;
 
-extern "C" int omg_softmax_rows(void* x, long long rows, int cols, long long ld, float scale, void* stream_) {
+static int softmax_rows_impl(void* x, long long rows, int cols, long long ld, float scale, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     OMG_CHECK(x && rows >= 1 && rows <= 0x7fffffffLL, "omg_softmax_rows: bad arguments");
     OMG_CHECK(cols >= 8 && cols % 8 == 0 && cols <= SM_THREADS * SM_MAXV * 8 && ld % 8 == 0 && ld >= cols,
@@ -240,7 +240,7 @@ extern "C" int omg_softmax_rows(void* x, long long rows, int cols, long long ld,
     return check_launch("softmax_rows_kernel");
 }
 
-extern "C" int omg_axpy(const void* a, const void* b, float alpha, void* y, long long n, void* stream_) {
+static int axpy_impl(const void* a, const void* b, float alpha, void* y, long long n, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     OMG_CHECK(a && b && y && n > 0 && n % 8 == 0, "omg_axpy: bad arguments");
     const long long nvec = n / 8;
@@ -249,7 +249,7 @@ extern "C" int omg_axpy(const void* a, const void* b, float alpha, void* y, long
     return check_launch("axpy_kernel");
 }
 
-extern "C" int omg_fuse_step(const omg_fuse_desc* d, void* stream_) {
+static int fuse_step_impl(const omg_fuse_desc* d, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     OMG_CHECK(d && d->noise_main && d->latents, "omg_fuse_step: null pointer");
     OMG_CHECK(d->n_concepts >= 0 && d->n_concepts <= OMG_MAX_CONCEPTS, "omg_fuse_step: n_concepts=%d out of range",
@@ -276,10 +276,38 @@ extern "C" int omg_fuse_step(const omg_fuse_desc* d, void* stream_) {
     return check_launch("fuse_step_kernel");
 }
 
-extern "C" int omg_ctx_mix(const void* ctx, const void* coef, void* out, int B, int L, int C, void* stream_) {
+static int ctx_mix_impl(const void* ctx, const void* coef, void* out, int B, int L, int C, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     OMG_CHECK(ctx && coef && out && B >= 1 && L >= 1 && C >= 1, "omg_ctx_mix: bad arguments");
     OMG_CUDA(launch_pdl(ctx_mix_kernel, dim3((C + 127) / 128, L, B), dim3(128), 0, stream,
                         static_cast<const __half*>(ctx), static_cast<const float*>(coef), static_cast<__half*>(out), L, C));
     return check_launch("ctx_mix_kernel");
+}
+
+// C-ABI entry points: launch, and - while this thread records a launch plan (omg_plan_record_begin) - remember the call
+extern "C" int omg_softmax_rows(void* x, long long rows, int cols, long long ld, float scale, void* stream_) {
+    const int rc = softmax_rows_impl(x, rows, cols, ld, scale, stream_);
+    if (rc == 0 && ::omg::plan_recording()) ::omg::plan_note([=](void* s) { return softmax_rows_impl(x, rows, cols, ld, scale, s); });
+    return rc;
+}
+
+extern "C" int omg_axpy(const void* a, const void* b, float alpha, void* y, long long n, void* stream_) {
+    const int rc = axpy_impl(a, b, alpha, y, n, stream_);
+    if (rc == 0 && ::omg::plan_recording()) ::omg::plan_note([=](void* s) { return axpy_impl(a, b, alpha, y, n, s); });
+    return rc;
+}
+
+extern "C" int omg_fuse_step(const omg_fuse_desc* d, void* stream_) {
+    const int rc = fuse_step_impl(d, stream_);
+    if (rc == 0 && ::omg::plan_recording()) {
+        const omg_fuse_desc c = *d;  // by value: a plan outlives the caller's descriptor
+        ::omg::plan_note([c](void* s) { return fuse_step_impl(&c, s); });
+    }
+    return rc;
+}
+
+extern "C" int omg_ctx_mix(const void* ctx, const void* coef, void* out, int B, int L, int C, void* stream_) {
+    const int rc = ctx_mix_impl(ctx, coef, out, B, L, C, stream_);
+    if (rc == 0 && ::omg::plan_recording()) ::omg::plan_note([=](void* s) { return ctx_mix_impl(ctx, coef, out, B, L, C, s); });
+    return rc;
 }

@@ -701,7 +701,7 @@ extern "C" int omg_gemm_colstats_blocks(int W, int H) {
     return ((W + tw - 1) / tw) * ((H + th - 1) / th) * 4;
 }
 
-extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
+static int gemm_impl(const omg_gemm_desc* d, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     OMG_CHECK(d != nullptr, "omg_gemm: null descriptor");
     OMG_CHECK(d->n_a >= 1 && d->n_a <= OMG_MAX_A, "omg_gemm: n_a=%d out of range", d->n_a);
@@ -887,4 +887,14 @@ extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
         case 160: return launch_gemm<160, OMG_EPI_NONE, 1>(p, stream);
         default: return launch_gemm<256, OMG_EPI_NONE, 1>(p, stream);
     }
+}
+
+// C-ABI entry points: launch, and - while this thread records a launch plan (omg_plan_record_begin) - remember the call
+extern "C" int omg_gemm(const omg_gemm_desc* d, void* stream_) {
+    const int rc = gemm_impl(d, stream_);
+    if (rc == 0 && ::omg::plan_recording()) {
+        const omg_gemm_desc c = *d;  // by value: a plan outlives the caller's descriptor
+        ::omg::plan_note([c](void* s) { return gemm_impl(&c, s); });
+    }
+    return rc;
 }

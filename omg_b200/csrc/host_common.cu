@@ -2,7 +2,10 @@
 
 #include <stdlib.h>
 
+#include <new>
+
 #include <mutex>
+#include <vector>
 
 #include "../../include/omg_b200.h"
 
@@ -59,6 +62,57 @@ int make_tmap_f16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* d
 }
 
 }  // namespace omg
+
+// ------------------------------------------------------------------------------------------------ launch plans
+struct omg_plan {
+    std::vector<std::function<int(void*)>> steps;
+};
+
+namespace omg {
+static thread_local omg_plan* g_recording = nullptr;
+bool plan_recording() { return g_recording != nullptr; }
+void plan_note(std::function<int(void*)> step) {
+    if (g_recording) g_recording->steps.push_back(std::move(step));
+}
+}  // namespace omg
+
+extern "C" omg_plan* omg_plan_create(void) { return new (std::nothrow) omg_plan(); }
+
+extern "C" void omg_plan_destroy(omg_plan* plan) {
+    if (plan && omg::g_recording == plan) omg::g_recording = nullptr;
+    delete plan;
+}
+
+extern "C" int omg_plan_record_begin(omg_plan* plan) {
+    OMG_CHECK(plan != nullptr, "omg_plan_record_begin: null plan");
+    OMG_CHECK(omg::g_recording == nullptr, "omg_plan_record_begin: this thread is already recording a plan");
+    omg::g_recording = plan;
+    return 0;
+}
+
+extern "C" int omg_plan_record_end(omg_plan* plan) {
+    OMG_CHECK(plan != nullptr && omg::g_recording == plan, "omg_plan_record_end: this plan is not being recorded on this thread");
+    omg::g_recording = nullptr;
+    return 0;
+}
+
+extern "C" int omg_plan_length(const omg_plan* plan) { return plan ? (int)plan->steps.size() : -1; }
+
+extern "C" int omg_plan_clear(omg_plan* plan) {
+    OMG_CHECK(plan != nullptr && omg::g_recording != plan, "omg_plan_clear: null plan, or the plan is being recorded");
+    plan->steps.clear();
+    return 0;
+}
+
+extern "C" int omg_plan_run(const omg_plan* plan, void* stream) {
+    OMG_CHECK(plan != nullptr, "omg_plan_run: null plan");
+    OMG_CHECK(omg::g_recording != plan, "omg_plan_run: the plan is still being recorded");
+    for (const auto& step : plan->steps) {
+        const int rc = step(stream);
+        if (rc != 0) return rc;  // omg_last_error() holds the failing launch's message
+    }
+    return 0;
+}
 
 extern "C" const char* omg_last_error(void) { return omg::g_err; }
 extern "C" const char* omg_version(void) { return "omg_b200 0.1 sm_100a"; }

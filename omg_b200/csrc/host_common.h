@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <functional>
 
 namespace omg {
 
@@ -38,6 +39,11 @@ inline int check_launch(const char* what) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
+
+// Launch plans (omg_plan_*, include/omg_b200.h): while a thread records, every entry point that launched successfully also
+// appends a replayable copy of its call (descriptors by value) to the plan; omg_plan_run re-issues them on a stream.
+bool plan_recording();
+void plan_note(std::function<int(void*)> step);
 
 // Every kernel of this library can be launched with programmatic dependent launch (PDL): the next kernel's CTAs may
 // become resident and run their prologue (barrier init, TMEM alloc, descriptor prefetch) while the previous kernel

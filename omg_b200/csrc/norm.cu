@@ -373,7 +373,7 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __r
 
 using namespace omg;
 
-extern "C" int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, const void* gamma,
+static int groupnorm_impl(const void* x1, int C1, const void* x2, int C2, int B, int HW, const void* gamma,
                              const void* beta, float eps, int silu, void* stats_ws, void* y, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     const int C = C1 + C2;
@@ -414,7 +414,7 @@ extern "C" int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int
     return launch_gn_apply(s, B, HW, silu, ab, static_cast<__half*>(y), stream);
 }
 
-extern "C" int omg_colstats(const void* x, int C, int B, int HW, void* out, void* stream_) {
+static int colstats_impl(const void* x, int C, int B, int HW, void* out, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     OMG_CHECK(x && out, "omg_colstats: null pointer");
     OMG_CHECK(C >= 8 && C % 8 == 0 && B >= 1 && HW >= 1, "omg_colstats: bad shape");
@@ -424,7 +424,7 @@ extern "C" int omg_colstats(const void* x, int C, int B, int HW, void* out, void
     return check_launch("colstats_kernel");
 }
 
-extern "C" int omg_groupnorm_apply(const void* x1, int C1, const void* part1, int rb1, const void* x2, int C2,
+static int groupnorm_apply_impl(const void* x1, int C1, const void* part1, int rb1, const void* x2, int C2,
                                    const void* part2, int rb2, int B, int HW, const void* gamma, const void* beta, float eps,
                                    int silu, void* stats_ws, void* y, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -443,7 +443,7 @@ extern "C" int omg_groupnorm_apply(const void* x1, int C1, const void* part1, in
     return launch_gn_apply(s, B, HW, silu, ab, static_cast<__half*>(y), stream);
 }
 
-extern "C" int omg_layernorm(const void* x, const void* gamma, const void* beta, void* y, long long rows, int C,
+static int layernorm_impl(const void* x, const void* gamma, const void* beta, void* y, long long rows, int C,
                              float eps, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     OMG_CHECK(x && gamma && beta && y, "omg_layernorm: null pointer");
@@ -463,4 +463,33 @@ extern "C" int omg_layernorm(const void* x, const void* gamma, const void* beta,
     else
         OMG_CUDA(launch_pdl(layernorm_kernel<10>, dim3(grid), dim3(warps * 32), 0, stream, xp, gp, bp, yp, rows, C, eps));
     return check_launch("layernorm_kernel");
+}
+
+// C-ABI entry points: launch, and - while this thread records a launch plan (omg_plan_record_begin) - remember the call
+extern "C" int omg_groupnorm(const void* x1, int C1, const void* x2, int C2, int B, int HW, const void* gamma,
+                             const void* beta, float eps, int silu, void* stats_ws, void* y, void* stream_) {
+    const int rc = groupnorm_impl(x1, C1, x2, C2, B, HW, gamma, beta, eps, silu, stats_ws, y, stream_);
+    if (rc == 0 && ::omg::plan_recording()) ::omg::plan_note([=](void* s) { return groupnorm_impl(x1, C1, x2, C2, B, HW, gamma, beta, eps, silu, stats_ws, y, s); });
+    return rc;
+}
+
+extern "C" int omg_colstats(const void* x, int C, int B, int HW, void* out, void* stream_) {
+    const int rc = colstats_impl(x, C, B, HW, out, stream_);
+    if (rc == 0 && ::omg::plan_recording()) ::omg::plan_note([=](void* s) { return colstats_impl(x, C, B, HW, out, s); });
+    return rc;
+}
+
+extern "C" int omg_groupnorm_apply(const void* x1, int C1, const void* part1, int rb1, const void* x2, int C2,
+                                   const void* part2, int rb2, int B, int HW, const void* gamma, const void* beta, float eps,
+                                   int silu, void* stats_ws, void* y, void* stream_) {
+    const int rc = groupnorm_apply_impl(x1, C1, part1, rb1, x2, C2, part2, rb2, B, HW, gamma, beta, eps, silu, stats_ws, y, stream_);
+    if (rc == 0 && ::omg::plan_recording()) ::omg::plan_note([=](void* s) { return groupnorm_apply_impl(x1, C1, part1, rb1, x2, C2, part2, rb2, B, HW, gamma, beta, eps, silu, stats_ws, y, s); });
+    return rc;
+}
+
+extern "C" int omg_layernorm(const void* x, const void* gamma, const void* beta, void* y, long long rows, int C,
+                             float eps, void* stream_) {
+    const int rc = layernorm_impl(x, gamma, beta, y, rows, C, eps, stream_);
+    if (rc == 0 && ::omg::plan_recording()) ::omg::plan_note([=](void* s) { return layernorm_impl(x, gamma, beta, y, rows, C, eps, s); });
+    return rc;
 }

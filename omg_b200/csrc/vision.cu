@@ -240,7 +240,7 @@ __global__ void resize_bicubic_kernel(const __half* __restrict__ x, __half* __re
 
 using namespace omg;
 
-extern "C" int omg_dwconv(const void* x, const void* w, const void* bias, void* y, int B, int H, int W, int C, int ldx, int ldy,
+static int dwconv_impl(const void* x, const void* w, const void* bias, void* y, int B, int H, int W, int C, int ldx, int ldy,
                           int ksize, int stride, int act, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     OMG_CHECK(x && w && y, "omg_dwconv: null pointer");
@@ -259,7 +259,7 @@ extern "C" int omg_dwconv(const void* x, const void* w, const void* bias, void* 
     return check_launch("dwconv_kernel");
 }
 
-extern "C" int omg_group1x1(const void* x, const void* w, void* y, long long pixels, int C, int ldx, int ldy, int group,
+static int group1x1_impl(const void* x, const void* w, void* y, long long pixels, int C, int ldx, int ldy, int group,
                             void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     OMG_CHECK(x && w && y, "omg_group1x1: null pointer");
@@ -271,7 +271,7 @@ extern "C" int omg_group1x1(const void* x, const void* w, void* y, long long pix
     return check_launch("group1x1_kernel");
 }
 
-extern "C" int omg_relu_linear_attention(const void* qkv, void* out, int B, int N, int heads, int dim, float eps, void* stream_) {
+static int relu_linear_attention_impl(const void* qkv, void* out, int B, int N, int heads, int dim, float eps, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     OMG_CHECK(qkv && out, "omg_relu_linear_attention: null pointer");
     OMG_CHECK(dim == 32 && B >= 1 && N >= 1 && heads >= 1, "omg_relu_linear_attention: head dim 32 only (EfficientViT-SAM)");
@@ -280,7 +280,7 @@ extern "C" int omg_relu_linear_attention(const void* qkv, void* out, int B, int 
     return check_launch("relu_linear_attn_kernel");
 }
 
-extern "C" int omg_resize_bicubic(const void* x, void* y, int B, int H, int W, int C, int Ho, int Wo, void* stream_) {
+static int resize_bicubic_impl(const void* x, void* y, int B, int H, int W, int C, int Ho, int Wo, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     OMG_CHECK(x && y, "omg_resize_bicubic: null pointer");
     OMG_CHECK(B >= 1 && H >= 1 && W >= 1 && Ho >= 1 && Wo >= 1 && C >= 8 && C % 8 == 0, "omg_resize_bicubic: bad shape");
@@ -289,4 +289,31 @@ extern "C" int omg_resize_bicubic(const void* x, void* y, int B, int H, int W, i
                         static_cast<const __half*>(x), static_cast<__half*>(y), H, W, C, Ho, Wo, (float)H / (float)Ho,
                         (float)W / (float)Wo));
     return check_launch("resize_bicubic_kernel");
+}
+
+// C-ABI entry points: launch, and - while this thread records a launch plan (omg_plan_record_begin) - remember the call
+extern "C" int omg_dwconv(const void* x, const void* w, const void* bias, void* y, int B, int H, int W, int C, int ldx, int ldy,
+                          int ksize, int stride, int act, void* stream_) {
+    const int rc = dwconv_impl(x, w, bias, y, B, H, W, C, ldx, ldy, ksize, stride, act, stream_);
+    if (rc == 0 && ::omg::plan_recording()) ::omg::plan_note([=](void* s) { return dwconv_impl(x, w, bias, y, B, H, W, C, ldx, ldy, ksize, stride, act, s); });
+    return rc;
+}
+
+extern "C" int omg_group1x1(const void* x, const void* w, void* y, long long pixels, int C, int ldx, int ldy, int group,
+                            void* stream_) {
+    const int rc = group1x1_impl(x, w, y, pixels, C, ldx, ldy, group, stream_);
+    if (rc == 0 && ::omg::plan_recording()) ::omg::plan_note([=](void* s) { return group1x1_impl(x, w, y, pixels, C, ldx, ldy, group, s); });
+    return rc;
+}
+
+extern "C" int omg_relu_linear_attention(const void* qkv, void* out, int B, int N, int heads, int dim, float eps, void* stream_) {
+    const int rc = relu_linear_attention_impl(qkv, out, B, N, heads, dim, eps, stream_);
+    if (rc == 0 && ::omg::plan_recording()) ::omg::plan_note([=](void* s) { return relu_linear_attention_impl(qkv, out, B, N, heads, dim, eps, s); });
+    return rc;
+}
+
+extern "C" int omg_resize_bicubic(const void* x, void* y, int B, int H, int W, int C, int Ho, int Wo, void* stream_) {
+    const int rc = resize_bicubic_impl(x, y, B, H, W, C, Ho, Wo, stream_);
+    if (rc == 0 && ::omg::plan_recording()) ::omg::plan_note([=](void* s) { return resize_bicubic_impl(x, y, B, H, W, C, Ho, Wo, s); });
+    return rc;
 }

@@ -34,6 +34,41 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+class LaunchPlan:
+    """omg_plan (include/omg_b200.h): the launches of one forward recorded at the C ABI and replayed from C with no
+    descriptor building - what a non-Python host holds instead of the reference's `self.unet(...)` call
+    (src/pipelines/lora_pipeline.py:558-567).  Everything a recorded launch points to must outlive the plan (the
+    executor's persistent workspace does; tensors allocated inside the recorded region do not)."""
+
+    def __init__(self):
+        self._lib = L.load()
+        self._h = self._lib.omg_plan_create()
+        if not self._h:
+            raise RuntimeError("omg_plan_create failed")
+
+    def __enter__(self):
+        L.check(self._lib.omg_plan_record_begin(self._h), "omg_plan_record_begin")
+        return self
+
+    def __exit__(self, *exc):
+        L.check(self._lib.omg_plan_record_end(self._h), "omg_plan_record_end")
+        return False
+
+    def __len__(self):
+        return int(self._lib.omg_plan_length(self._h))
+
+    def clear(self):
+        L.check(self._lib.omg_plan_clear(self._h), "omg_plan_clear")
+
+    def run(self, stream=None):
+        L.check(self._lib.omg_plan_run(self._h, _stream() if stream is None else stream), "omg_plan_run")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.omg_plan_destroy(h)
+
+
 def gemm(a_views, segs, w, N, Ktot, d_view, bias=None, rowvec=None, rowvec_ld=0, residual=None, residual_ld=0,
          epilogue=L.EPI_NONE, block_n=0, w2=None, stats_out=None, ln=None, cta_pair=0, row_groups=None, colstats=None,
          residual_f32=None, out_f32=None):

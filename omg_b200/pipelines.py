@@ -189,6 +189,11 @@ class _BasePipeline:
         self.vae_decoder = vae_decoder
         self.scheduler = EulerDiscreteSchedule()
         self.use_graphs = use_graphs
+        # how a UNet forward is issued: "graph" (CUDA graphs, the default), "plan" (C-ABI launch plans, omg_plan: recorded
+        # once, replayed from C - the executor for hosts without graph plumbing) or "eager"; OMG_EXECUTOR overrides
+        self.executor = (os.environ.get("OMG_EXECUTOR") or "graph") if use_graphs else "eager"
+        if self.executor not in ("graph", "plan", "eager"):
+            raise ValueError(f"unknown executor {self.executor!r} (graph | plan | eager)")
         self.controller: Optional[AttentionReplace] = None
         self.main_lora_key: Optional[str] = None
         self._runners: Dict[tuple, UNetRunner] = {}
@@ -235,7 +240,8 @@ class _BasePipeline:
         key = (tag, id(model), batch, h, w, lora_key, tag_extra, self.trunk_f32)
         r = self._runners.get(key)
         if r is None:
-            r = UNetRunner(model, batch, h, w, lora_key=lora_key, use_graphs=self.use_graphs, groups=groups)
+            r = UNetRunner(model, batch, h, w, lora_key=lora_key, use_graphs=self.executor == "graph", groups=groups,
+                           use_plans=self.executor == "plan")
             if self.trunk_f32 is not None:
                 r.trunk_f32 = bool(self.trunk_f32)
             self._runners[key] = r

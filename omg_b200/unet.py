@@ -265,7 +265,7 @@ class UNetRunner:
     CUDA graphs per variant."""
 
     def __init__(self, model: PackedUNet, batch: int, H: int, W: int, lora_key: Optional[str] = None,
-                 use_graphs: bool = True, groups: Optional[List[RowGroup]] = None):
+                 use_graphs: bool = True, groups: Optional[List[RowGroup]] = None, use_plans: bool = False):
         self.m, self.B, self.H, self.W = model, batch, H, W
         self.groups = groups or [RowGroup(0, batch, lora_key, model.ip is not None)]
         self._b2_cache: Dict[str, object] = {}
@@ -283,6 +283,10 @@ class UNetRunner:
         self.dev = model.device
         self.ws: Dict[str, torch.Tensor] = {}
         self.use_graphs = use_graphs
+        # use_plans (with use_graphs=False): every forward variant is recorded once as a C-ABI launch plan (omg_plan) and
+        # replayed from C - the executor a host without CUDA-graph plumbing (or without Python) drives
+        self.use_plans = use_plans and not use_graphs
+        self.plans: Dict[tuple, "ops.LaunchPlan"] = {}
         self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.graph_launches: Dict[tuple, int] = {}
         self.warm: set = set()
@@ -305,7 +309,8 @@ class UNetRunner:
 
     # ------------------------------------------------------------------------------------------- buffers
     def drop_graphs(self):
-        """Forget every captured graph (they hold raw device pointers and launch-time scalars)."""
+        """Forget every captured graph / recorded launch plan (they hold raw device pointers and launch-time scalars)."""
+        self.plans.clear()
         self.graphs.clear()
         self.graph_launches.clear()
         self.warm.clear()
@@ -747,6 +752,22 @@ class UNetRunner:
         variant = variant or self.default_variant()
         self.temb_step.copy_(self.temb_table[step_index])
         fn = self._forward_controlnet if self.m.controlnet else self._forward_unet
+        if self.use_plans and key is not None:
+            if self._graph_version != self.m.adapter_version:
+                self.drop_graphs()
+                self._graph_version = self.m.adapter_version
+            if key in self.plans:
+                self.plans[key].run()
+                return self._out[key]
+            if key not in self.warm:
+                self.warm.add(key)
+                self._out[key] = fn(variant)  # eager run: allocates the persistent buffers, builds the weight caches
+                return self._out[key]
+            plan = ops.LaunchPlan()
+            with plan:
+                self._out[key] = fn(variant)  # launches AND records
+            self.plans[key] = plan
+            return self._out[key]
         if not self.use_graphs or key is None:
             return fn(variant)
         if self._graph_version != self.m.adapter_version:  # adapters / IP scale changed since the graphs were captured

@@ -12,7 +12,8 @@ import sys
 VARIANTS = [("default", {}), ("gn_stats_pass", {"OMG_GN_FUSE": "0"}),
             ("cross_per_head_ctas", {"OMG_ATTN_CROSS": "0"}), ("trunk_fp32_twins", {"OMG_TRUNK_F32": "1"}),
             ("attn_per_tile_ctas", {"OMG_ATTN_PERSISTENT": "0"}),
-            ("r01_equivalent", {"OMG_GN_FUSE": "0", "OMG_ATTN_CROSS": "0", "OMG_ATTN_PERSISTENT": "0"})]
+            ("r01_equivalent", {"OMG_GN_FUSE": "0", "OMG_ATTN_CROSS": "0", "OMG_ATTN_PERSISTENT": "0"}),
+            ("launch_plan_executor", {"OMG_EXECUTOR": "plan"})]
 if "--variants" in sys.argv:
     want = sys.argv[sys.argv.index("--variants") + 1].split(",")
     VARIANTS = [v for v in VARIANTS if v[0] in want]
@@ -47,6 +48,17 @@ def one():
             torch.cuda.synchronize()
             out[f"{tag[0]}_b{tag[2]}:{'/'.join(str(k) for k in key)}"] = {"ms": round(e0.elapsed_time(e1) / 10, 3),
                                                                            "launches": r.graph_launches[key]}
+        for key, pl in r.plans.items():   # OMG_EXECUTOR=plan: the forward replayed from C (omg_plan_run), no CUDA graph
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(3):
+                pl.run()
+            e0.record()
+            for _ in range(10):
+                pl.run()
+            e1.record()
+            torch.cuda.synchronize()
+            out[f"{tag[0]}_b{tag[2]}:{'/'.join(str(k) for k in key)}"] = {"ms": round(e0.elapsed_time(e1) / 10, 3),
+                                                                           "launches": len(pl), "executor": "plan"}
     print(json.dumps(out))
 
 

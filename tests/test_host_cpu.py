@@ -31,6 +31,29 @@ def test_library_exports_every_declared_symbol():
     assert l2.omg_launch_count() == 0
 
 
+def test_launch_plan_handle_protocol():
+    """omg_plan_* (the forward-as-a-handle boundary): create / record / run / destroy and their error strings; no launch
+    entry point is called, so nothing here needs a GPU."""
+    from omg_b200 import _lib as L
+    from omg_b200 import ops
+    lib = L.load()
+    plan = ops.LaunchPlan()
+    assert len(plan) == 0
+    plan.run(0)                                              # an empty plan runs (no CUDA call behind it)
+    with plan:
+        with pytest.raises(RuntimeError, match="already recording"):
+            ops.LaunchPlan().__enter__()                     # one recording per thread
+        assert lib.omg_plan_run(plan._h, None) == 1 and b"still being recorded" in lib.omg_last_error()
+        assert lib.omg_plan_clear(plan._h) == 1
+        # a call that fails validation is not recorded
+        assert lib.omg_gemm(None, None) == 1
+    assert len(plan) == 0
+    assert lib.omg_plan_record_end(plan._h) == 1 and b"not being recorded" in lib.omg_last_error()
+    assert lib.omg_plan_length(None) == -1
+    assert lib.omg_plan_run(None, None) == 1 and b"null plan" in lib.omg_last_error()
+    plan.clear()
+
+
 def test_struct_sizes_match_c_layout():
     """ctypes mirrors of the descriptors must have the C sizes (checked against a compile-time table)."""
     from omg_b200 import _lib

@@ -286,6 +286,12 @@ def test_main_pass_controlnet_condition_change_with_graphs():
     outs = [pipe(image=[c, c], concept_models=cm, **common).images.clone() for c in conds]
     outs.append(pipe(image=[conds[0], conds[0]], concept_models=cm, **common).images.clone())   # back to the first image
     assert torch.equal(outs[0], outs[2]) and not torch.equal(outs[0], outs[1])
+    # the same loop with every forward replayed from a C-ABI launch plan (omg_plan) instead of a CUDA graph
+    planned, cm3 = build(False)
+    planned.executor = "plan"
+    for k, c in enumerate(conds):
+        assert rel(planned(image=[c, c], concept_models=cm3, **common).images, outs[k]) < 1e-5
+    assert sum(len(r.plans) for r in planned._runners.values()) >= 2 and not any(r.graphs for r in planned._runners.values())
     pe, ne, pp, np_ = pipe.encode_prompt(["p"] * 2, ["n"] * 2)
     tid = torch.tensor([[size, size, 0, 0, size, size]], dtype=torch.float32)
     for k, c in enumerate(conds):

@@ -83,6 +83,43 @@ def test_graph_replay_matches_eager(env):
     assert torch.equal(a, b) and torch.equal(b, c)
 
 
+def test_launch_plan_replay_matches_eager(env):
+    """The forward as a C-ABI handle (omg_plan): recorded once, replayed from C.  Bit-identical to the eager launches, one
+    plan step per entry-point call (omg_groupnorm_apply is two kernels), no pointer into freed memory (the allocator is churned between recording and replay),
+    and a replay recomputes (a new input gives the eager result for that input)."""
+    from omg_b200 import _lib as L
+    from omg_b200.unet import UNetRunner
+    cfg = env["cfg"]
+    B, H, W = 2, 32, 32
+    x, ctx, pooled, tid = _inputs(cfg, B, H, W, 2)
+    x2 = _inputs(cfg, B, H, W, 3)[0]
+    e = UNetRunner(env["model"], B, H, W, use_graphs=False)
+    e.set_conditioning([333.0], ctx, pooled, tid)
+    e.sample_in.copy_(to_nhwc8(x))
+    n0 = L.launch_count()
+    ref1 = e.forward(0).clone()
+    launches = L.launch_count() - n0
+    e.sample_in.copy_(to_nhwc8(x2))
+    ref2 = e.forward(0).clone()
+    r = UNetRunner(env["model"], B, H, W, use_graphs=False, use_plans=True)
+    r.set_conditioning([333.0], ctx, pooled, tid)
+    r.sample_in.copy_(to_nhwc8(x))
+    a = r.forward(0, key=("k",)).clone()     # eager warm-up
+    b = r.forward(0, key=("k",)).clone()     # eager + recording
+    assert 0 < len(r.plans[("k",)]) <= launches
+    junk = [torch.randn(1 << 20, device="cuda") for _ in range(16)]   # churn the caching allocator
+    del junk
+    junk = [torch.full((3 << 18,), float("nan"), device="cuda") for _ in range(24)]
+    n1 = L.launch_count()
+    c = r.forward(0, key=("k",)).clone()     # replay from C
+    assert L.launch_count() - n1 == launches
+    assert torch.equal(a, ref1) and torch.equal(b, ref1) and torch.equal(c, ref1)
+    r.sample_in.copy_(to_nhwc8(x2))
+    d = r.forward(0, key=("k",)).clone()
+    assert torch.equal(d, ref2) and not torch.equal(d, ref1)
+    del junk
+
+
 def test_main_unet_p2p(env):
     """B=4 rows (u0,u1,c0,c1) under AttentionReplace: self-replace window on (step 0) and off (step 25)."""
     from omg_b200.prompt_attention import AttentionReplace
