@@ -101,3 +101,8 @@ def test_sam_image_encoder_matches_the_reference_module():
     e3, e5, e = rel(feats[3], d["stage3"]), rel(feats[5], d["stage5"]), rel(y, d["y"])
     print("sam encoder rel err: stage3", e3, "stage5", e5, "output", e)
     assert e3 < 5.5e-4 and e5 < 6e-4 and e < 8.5e-4   # measured 4.1e-4 / 4.5e-4 / 6.5e-4
+    # the call above captured a CUDA graph; a replay on another image must equal the eager launches for that image bit for bit
+    x2 = d["x"].flip(-1) * 0.5
+    y2 = enc(x2, return_features=True)[0]
+    eager = PackedSamImageEncoder(d["sd"], device="cuda", use_graph=False)
+    assert torch.equal(y2, eager(x2)) and torch.equal(enc(d["x"], return_features=True)[0], y) and not torch.equal(y2, y)
