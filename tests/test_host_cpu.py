@@ -31,6 +31,24 @@ def test_library_exports_every_declared_symbol():
     assert l2.omg_launch_count() == 0
 
 
+def test_header_is_plain_c99_and_matches_the_ctypes_layout():
+    """include/omg_b200.h compiles as C99 (no C++, no CUDA headers: the boundary is plain pointers and sizes) and the
+    descriptor sizes the C compiler sees are the ones the ctypes binding uses."""
+    import shutil
+    import subprocess
+    import tempfile
+    from omg_b200 import _lib as L
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "abi_check")
+        subprocess.run([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c_host", "abi_check.c"), "-o", exe], check=True)
+        sizes = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(t) for t in (L.View4, L.Seg, L.GemmDesc, L.AttnDesc, L.FuseDesc)]
+
+
 def test_launch_plan_handle_protocol():
     """omg_plan_* (the forward-as-a-handle boundary): create / record / run / destroy and their error strings; no launch
     entry point is called, so nothing here needs a GPU."""
