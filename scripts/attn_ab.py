@@ -48,6 +48,13 @@ def main():
             out[tag]["sdpa_tflops"] = round(fl / ms2 / 1e9, 1)
             ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(B, N, C)
             out[tag]["rel_l2"] = float((o.float() - ref).norm() / ref.norm())
+    for (B, N, heads, Lk, tag) in [(4, 1024, 20, 77, "cross1024"), (4, 4096, 10, 77, "cross4096"), (4, 1024, 20, 16, "ip1024")]:
+        C = heads * 64
+        qx, kv = torch.randn(B, N, C, device=dev).half(), torch.randn(B, Lk, 2 * C, device=dev).half()
+        o = torch.empty(B, N, C, device=dev, dtype=torch.float16)
+        items = [(b, b, b, b) for b in range(B)]
+        ms = timeit(lambda: ops.attention(qx, kv, kv, o, heads, N, Lk, items, 0, 0, C))
+        out[tag] = {"us": round(ms * 1e3, 1)}
     print(json.dumps(out))
 
 
