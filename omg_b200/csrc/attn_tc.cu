@@ -20,7 +20,7 @@
 // Softmax follows the lazy-rescale scheme: O stays in TMEM and is accumulated by the tensor core across KV blocks;
 // the running maximum is allowed to go stale by up to 2^8 and O is only rescaled (TMEM load-scale-store) when a row
 // maximum grows beyond that, which after the first blocks is rare.  The arithmetic is packed fp32x2 (FFMA2 / FADD2);
-// exp2 runs on the MUFU for 11 of 16 element pairs and as a degree-3 polynomial on the FMA pipe for the other 5
+// exp2 runs on the MUFU for 14 of 16 element pairs and as a degree-3 polynomial on the FMA pipe for the other 2
 // (MUFU only: 529 TFLOP/s; ncu in profiles/r01_ncu_full_summary.csv).
 #include <cuda_fp16.h>
 
@@ -34,9 +34,11 @@
 #include "ptx.cuh"
 
 // which of the 16 element pairs of a 32-column chunk take the polynomial exp2 (FMA pipe) instead of the MUFU:
-// balances issue slots (5 per polynomial value) against the MUFU's 16 lanes / clk / SM; 5 of 16 pairs by default
+// balances issue slots (5 per polynomial value) against the MUFU's 16 lanes / clk / SM.  Round 1 (one CTA per tile) settled
+// on 5 of 16; with the persistent kernel a same-box sweep (profiles/r02_attn_variants.jsonl) has 2 of 16 ahead on all four
+// SDXL shapes (+2..4 %; all-MUFU is best at B = 4 and worst at B = 8, where the longer launch runs into the power cap)
 #ifndef OMG_ATT_POLY_MASK
-#define OMG_ATT_POLY_MASK 0x4924
+#define OMG_ATT_POLY_MASK 0x0101
 #endif
 
 namespace omg {
