@@ -76,6 +76,9 @@ struct alignas(64) AttnParams {
     float out_weight;
     int accumulate;
     int causal;  // cross kernel only: key index > query index is masked
+#ifdef OMG_ATT_TRACE
+    long long* trace;  // [cta < 2][role 2][block 512][8] clock stamps (diagnostic build only)
+#endif
 };
 
 // Pipeline (per 128-row tile g, KV block j, buffer b = j & 1):
@@ -481,9 +484,20 @@ __global__ void __launch_bounds__(256, 2) attn_p_kernel(const __grid_constant__ 
                 int ti = 0, j = 0;
                 for (uint32_t g = 0; g < total; ++g) {
                     const int b = g & 1;
+#ifdef OMG_ATT_TRACE
+                    const bool tr = p.trace && (blockIdx.x == 0 || blockIdx.x == 148) && g < 512;
+                    long long* tp = tr ? p.trace + (((blockIdx.x ? 1 : 0) * 2 + 1) * 512 + g) * 8 : nullptr;
+                    if (tr) tp[0] = clock64();
+#endif
                     mbar_wait(&p_full[b], (g >> 1) & 1);
                     tc_fence_after();
+#ifdef OMG_ATT_TRACE
+                    if (tr) tp[1] = clock64();
+#endif
                     if (sg < total) issue_s();
+#ifdef OMG_ATT_TRACE
+                    if (tr) tp[2] = clock64();
+#endif
                     if (j == 0 && ti > 0) {  // O still holds the previous tile until the softmax group has read it
                         mbar_wait(o_free, (ti - 1) & 1);
                         tc_fence_after();
@@ -496,6 +510,9 @@ __global__ void __launch_bounds__(256, 2) attn_p_kernel(const __grid_constant__ 
                     tc_commit(&p_empty[b]);
                     tc_commit(&kv_empty[g % KVS]);
                     if (j == nkv - 1) tc_commit(o_done);
+#ifdef OMG_ATT_TRACE
+                    if (tr) tp[3] = clock64();
+#endif
                     if (++j == nkv) {
                         j = 0;
                         ++ti;
@@ -521,13 +538,24 @@ __global__ void __launch_bounds__(256, 2) attn_p_kernel(const __grid_constant__ 
             float m = -INFINITY, l = 0.f;
             for (int j = 0; j < nkv; ++j, ++g) {
                 const int b = g & 1;
+#ifdef OMG_ATT_TRACE
+                const bool tr = p.trace && warp == 4 && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 148) && g < 512;
+                long long* tp = tr ? p.trace + (((blockIdx.x ? 1 : 0) * 2 + 0) * 512 + g) * 8 : nullptr;
+                if (tr) tp[0] = clock64();
+#endif
                 mbar_wait(&s_full[b], (g >> 1) & 1);
                 tc_fence_after();
+#ifdef OMG_ATT_TRACE
+                if (tr) tp[1] = clock64();
+#endif
                 const int kv_left = p.n_kv - j * ATT_BKV;
                 uint32_t sr[2][32];
                 tmem_ld_32x32(s_tmem + b * 64, sr[0]);
                 tmem_ld_32x32(s_tmem + b * 64 + 32, sr[1]);
                 tc_wait_ld();
+#ifdef OMG_ATT_TRACE
+                if (tr) tp[2] = clock64() + (long long)(sr[0][0] & 0u);
+#endif
                 if (kv_left < ATT_BKV) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
@@ -564,7 +592,13 @@ __global__ void __launch_bounds__(256, 2) attn_p_kernel(const __grid_constant__ 
                         tc_wait_st();
                     }
                 }
+#ifdef OMG_ATT_TRACE
+                if (tr) tp[3] = clock64() + (long long)(__float_as_uint(m) & 0u);
+#endif
                 if (g >= 2) mbar_wait(&p_empty[b], ((g >> 1) & 1) ^ 1);  // P[b] consumed by the P.V of running block g - 2
+#ifdef OMG_ATT_TRACE
+                if (tr) tp[4] = clock64();
+#endif
                 uint64_t sum2 = pack_f32x2(0.f, 0.f);
                 const uint64_t negm2 = pack_f32x2(-m, -m);
                 uint32_t pk[32];
@@ -586,14 +620,23 @@ __global__ void __launch_bounds__(256, 2) attn_p_kernel(const __grid_constant__ 
                         pk[c * 16 + i] = pack_half2(p0, p1);
                     }
                 }
+#ifdef OMG_ATT_TRACE
+                if (tr) tp[5] = clock64() + (long long)(pk[31] & 0u);
+#endif
                 tmem_st_32x32(p_tmem + b * 32, pk);
                 float sum, sum_hi;
                 unpack_f32x2(sum2, sum, sum_hi);
                 l += sum + sum_hi;
                 tc_wait_st();
+#ifdef OMG_ATT_TRACE
+                if (tr) tp[6] = clock64();
+#endif
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[b]);
+#ifdef OMG_ATT_TRACE
+                if (tr) tp[7] = clock64();
+#endif
             }
             // tile epilogue: O is complete once the last P.V has landed; read it out and hand TMEM back at once
             mbar_wait(o_done, ti & 1);
@@ -982,6 +1025,12 @@ static int attention_impl(const omg_attn_desc* d, void* stream_) {
     p.out_weight = d->out_weight;
     p.accumulate = d->accumulate;
     p.causal = d->causal;
+#ifdef OMG_ATT_TRACE
+    {
+        const char* e = getenv("OMG_ATT_TRACE_PTR");
+        p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+    }
+#endif
     OMG_CHECK(!d->causal || (d->n_kv <= 128 && d->n_q <= 128), "omg_attention: causal masking is available for sequences of <= 128 tokens");
     // Single-tile CTAs, two per SM, for every shape: two independent CTAs overlap each other's prologue / epilogue
     // with the other's main loop, which the two-tile CTA (tiles start and end together) cannot (measured, 5 KV
