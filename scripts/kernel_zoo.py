@@ -3,6 +3,7 @@ the target of ONE `ncu --set full --import-source on --nvtx --nvtx-include "zoo/
 (profiles/r02_ncu_kernel_table.csv is read out of that report).  Each launch is preceded by an NVTX marker range
 naming the shape, so the report rows can be told apart.
 """
+import os
 import sys
 
 import torch
@@ -105,6 +106,9 @@ lat = torch.randn(2, 128, 128, 4, device=dev)
 nxt, nxc = torch.empty(4, HW, 8, device=dev, dtype=torch.float16), torch.empty(2, HW, 8, device=dev, dtype=torch.float16)
 cases.append(("fuse_step (2 concepts) @128x128", lambda: ops.fuse_step(nm, nc, masks, 7.5, 5.0, 4.2, lat, nxt, nxc)))
 
+only = os.environ.get("OMG_ZOO_ONLY")   # substring filter: capture a subset (e.g. "self_attn") after a kernel change
+if only:
+    cases = [c for c in cases if only in c[0]]
 for name, fn in cases:   # warm-ups (kernel attributes, caches)
     fn()
     fn()
