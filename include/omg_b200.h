@@ -250,7 +250,8 @@ int omg_resize_bicubic(const void* x, void* y, int B, int H, int W, int C, int H
  * While a thread records, every entry point above that launched successfully also appends a copy of its call - the
  * descriptor by value, so every pointer in it must stay valid for as long as the plan is run (the executor's persistent
  * workspace does) - and omg_plan_run re-issues the calls in order on `stream` with no further host work than the launches.
- * Replay validates and encodes the descriptors again, so a plan stays valid across processes' lifetimes of the buffers only.
+ * Replay validates each descriptor and encodes its tensor maps again (a plan holds descriptors, not encoded launches), so a
+ * plan is valid exactly as long as the buffers its descriptors point to.
  * One recording per thread at a time; a plan may be run from any thread once recording has ended.
  */
 typedef struct omg_plan omg_plan;
