@@ -24,7 +24,6 @@ def one():
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from omg_b200 import factory
     from omg_b200.config import UNetConfig
-    from omg_b200.unet import RowGroup
     wl = factory.build_lora_workload(UNetConfig.sdxl(), 1024, 2, 32, 30, 7.5)
     pipe, cm, kw = wl.pipe, wl.concept_models, dict(wl.call_kwargs)
     lat0 = torch.randn(1, 4, 128, 128, generator=torch.Generator().manual_seed(14)).half()
